@@ -1,0 +1,76 @@
+// pass_params.h — host/device structures describing one pass (one kernel launch).
+//
+// A pass streams the resident particles of a snapshot once and deposits them into every lens plane that
+// uses this snapshot.  Planes that share a randomisation (Random.*[isnap], rcase — data.h:126-131,
+// slicer-v2.cpp:184-185) share an XformDev, so the box transform of gadget2io.cpp:204-270 is evaluated
+// once per particle and only the slab test (densitymaps.cpp:374) is per plane.
+#pragma once
+#include <stdint.h>
+#include "../../include/slicer_b200.h"
+
+struct XformDev
+{
+  double box;    // Header.boxsize (data.h:70)
+  double c[3];   // Random.x0,y0,z0 (data.h:128)
+  float boxf;    // == box when exact_f32
+  float cf[3];   // == c[] when exact_f32
+  float rcase;   // slicer-v2.cpp:137,185
+  float sgn[3];  // sign applied to output axis k (already permuted): Random.sgn of the raw axis feeding it
+  int perm[3];   // raw axis (0,1,2) feeding output axis k (x,y,z): Random.face, gadget2io.cpp:223-252
+  int exact_f32; // box and centre are float-representable: float ops reproduce the double chain bit for bit
+  int first_plane, nplanes; // planes [first_plane, first_plane+nplanes) of PassParams::pl use this transform
+  float zmin, zmax;         // union of those planes' slabs: cheap early-out
+  // --- conservative float screen of the pipelined kernel (deposit_pipelined.cuh) ---
+  // a_k = fma(raw[perm k], sinv[k], offs[k]) approximates (sgn*raw/box [+1 if sgn<0]) - centre_k to ~4e-7;
+  // one wrap (a<0 -> a+1) gives the box coordinate.  Particles the screen cannot decide are sent to the
+  // exact chain, never dropped.
+  float sinv[3];
+  float offs[3];
+  float tmax;       // max over this transform's planes of pre_tx (>= pre_ty)
+  float thr_m;      // additive slack of the lateral test: screen error + tmax * (z error)
+  float zlo_m, zhi_m; // zmin/zmax widened by the screen's error margin
+  float zamb;       // z-wrap ambiguity: |w - 0.5| > zamb  => undecidable
+  float raw_half, raw_amb; // |raw - raw_half| > raw_amb => raw within margin of a box face (or outside)
+};
+
+struct PlaneDev
+{
+  // slab (densitymaps.cpp:346-347,374): double(z) >= minDist && double(z) < maxDist, restated on floats:
+  // zlo = smallest float >= minDist, zhi = smallest float >= maxDist  =>  z >= zlo && z < zhi
+  float zlo, zhi;
+  // conservative float prefilter: an accepted replica satisfies |Y| <= Z*pre_ty and |X| <= Z*pre_tx (+ slack)
+  float pre_tx, pre_ty;
+  float npixf;
+  int npix;
+  int nrep;  // Lens.nrepperp (data.h:116)
+  int pow2;  // npix is a power of two: dl is exact, divisions by dl become exact multiplications
+  double T;          // fovradiants*(1.+2./npix)*0.5     densitymaps.cpp:383
+  double fovrad;     // densitymaps.cpp:385-386
+  double dl;         // 1./double(nn)                   utilities.cpp:50
+  double half_dl;    // 0.5*dx                          utilities.cpp:9
+  double onehalf_dl; // 0.5*3.0*dx                      utilities.cpp:11
+  double scale;      // 2^frac_bits
+  unsigned long long *acc;    // this plane's accumulators: [ntypes_alloc][npix*npix] int64 fixed point
+  unsigned long long *counts; // [SLICER_NTYPES][2]: accepted pairs, in-grid pairs
+  unsigned long long type_stride; // npix*npix when per-type maps are kept, else 0
+};
+
+struct PassParams
+{
+  int nxform;
+  int nplanes;
+  XformDev xf[SLICER_MAX_XFORMS];
+  PlaneDev pl[SLICER_MAX_PLANES];
+};
+
+struct SegmentDev
+{
+  const float *pos;  // AoS: n*3 floats; SoA: x[n_pad] y[n_pad] z[n_pad] with stride soa_stride
+  const float *mass; // n floats or nullptr
+  unsigned long long n;
+  unsigned long long soa_stride;
+  float const_mass; // float(massarr[type])            densitymaps.cpp:372
+  float max_m;      // MAX_M cut for per-particle mass  densitymaps.cpp:368
+  int type;
+  int layout;
+};

@@ -1,0 +1,896 @@
+// slicer_capi.cu — implementation of include/slicer_b200.h: handle, device memory, streams, pass set-up,
+// kernel launches, NCCL reduce.  Host-side arithmetic that feeds the kernel (minDist/maxDist, T, dl) is written
+// with the reference's own expressions so the doubles are bit-identical:
+//   densitymaps.cpp:346-347 (minDist,maxDist)  :383 (T)  utilities.cpp:50 (dl)  utilities.cpp:9,11 (0.5*dx, 0.5*3.0*dx)
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/slicer_b200.h"
+#include "pass_params.h"
+#include "aux_kernels.cuh"
+#include "deposit_simple.cuh"
+#include "deposit_pipelined.cuh"
+
+#define POS_U 1.0 /* gadget2io.h:14 */
+
+// ------------------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(const char *fmt, ...)
+{
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+#define CU(expr)                                                                                   \
+  do                                                                                               \
+  {                                                                                                \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__);     \
+  } while (0)
+
+extern "C" const char *slicer_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily so that single-GPU use has no dependency on it
+// ------------------------------------------------------------------------------------------------------------
+struct NcclApi
+{
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+  ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl()
+{
+  if (g_nccl.lib)
+    return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+  for (int i = 0; names[i] && !g_nccl.lib; i++)
+    g_nccl.lib = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!g_nccl.lib)
+    return fail("cannot load NCCL (libnccl.so.2): %s", dlerror());
+#define SYM(field, name)                                           \
+  *(void **)(&g_nccl.field) = dlsym(g_nccl.lib, name);             \
+  if (!g_nccl.field)                                               \
+  return fail("NCCL symbol %s missing", name)
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommInitAll, "ncclCommInitAll");
+  SYM(Reduce, "ncclReduce");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  return 0;
+}
+
+#define NC(expr)                                                                                        \
+  do                                                                                                    \
+  {                                                                                                     \
+    ncclResult_t _r = (expr);                                                                           \
+    if (_r != ncclSuccess)                                                                              \
+      return fail("%s failed: %s (%s:%d)", #expr, g_nccl.GetErrorString(_r), __FILE__, __LINE__);       \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------------------
+struct Segment
+{
+  int type;
+  size_t n;
+  const float *dpos;
+  const float *dmass;
+  int layout;
+  size_t soa_stride;
+};
+
+struct slicer_handle
+{
+  slicer_config cfg;
+  int frac_bits;
+  int ntypes_alloc;
+  size_t npix2max;
+  int sm_count;
+  cudaStream_t compute = nullptr, copy = nullptr;
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_copy = nullptr, ev_pass_done = nullptr;
+  float *d_pos = nullptr;  // particle_capacity * 3 floats (+pad)
+  float *d_mass = nullptr; // mass_capacity floats (+pad)
+  size_t pos_used = 0;     // in particles
+  size_t mass_used = 0;
+  std::vector<Segment> segs;
+  unsigned long long *d_acc = nullptr;    // [max_planes][ntypes_alloc][npix2max]
+  unsigned long long *d_counts = nullptr; // [max_planes][6][2]
+  float *d_out = nullptr;                 // npix2max
+  long long *d_sum = nullptr;             // npix2max
+  double boxsize = 0;
+  double massarr[SLICER_NTYPES] = {0, 0, 0, 0, 0, 0};
+  int hydro = 0;
+  int plane_npix[SLICER_MAX_PLANES];
+  bool have_timing = false;
+  bool copy_pending = false;
+  slicer_stats stats;
+  size_t device_bytes = 0;
+  ncclComm_t comm = nullptr;
+  int nranks = 1, rank = 0;
+  PipelinedScratch pipe;
+};
+
+static int set_device(slicer_handle *h)
+{
+  CU(cudaSetDevice(h->cfg.device));
+  return 0;
+}
+
+extern "C" int slicer_device_count(int *count)
+{
+  CU(cudaGetDeviceCount(count));
+  return 0;
+}
+
+extern "C" int slicer_alloc_pinned(size_t bytes, void **out)
+{
+  CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return 0;
+}
+
+extern "C" int slicer_free_pinned(void *p)
+{
+  CU(cudaFreeHost(p));
+  return 0;
+}
+
+template <typename T>
+static int dev_alloc(slicer_handle *h, T **p, size_t count)
+{
+  size_t bytes = count * sizeof(T);
+  CU(cudaMalloc((void **)p, bytes));
+  h->device_bytes += bytes;
+  return 0;
+}
+
+extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
+{
+  if (!cfg || !out)
+    return fail("slicer_create: null argument");
+  if (cfg->max_planes < 1 || cfg->max_planes > SLICER_MAX_PLANES)
+    return fail("slicer_create: max_planes must be 1..%d", SLICER_MAX_PLANES);
+  if (cfg->npix_max < 1)
+    return fail("slicer_create: npix_max must be positive");
+  if (cfg->mas != SLICER_MAS_TSC && cfg->mas != SLICER_MAS_NGP)
+    return fail("slicer_create: unknown mass-assignment scheme %d", cfg->mas);
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail("slicer_create: no usable CUDA device (%s); this library has no CPU path",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail("slicer_create: device %d out of range (have %d)", cfg->device, ndev);
+  slicer_handle *h = new slicer_handle;
+  h->cfg = *cfg;
+  h->frac_bits = cfg->frac_bits > 0 ? cfg->frac_bits : 40;
+  if (h->frac_bits > 60)
+  {
+    delete h;
+    return fail("slicer_create: frac_bits must be <= 60");
+  }
+  if (h->cfg.max_m <= 0)
+    h->cfg.max_m = 1e3; /* densitymaps.h:21 */
+  h->ntypes_alloc = cfg->per_type_maps ? SLICER_NTYPES : 1;
+  h->npix2max = (size_t)cfg->npix_max * (size_t)cfg->npix_max;
+  memset(&h->stats, 0, sizeof(h->stats));
+  memset(h->plane_npix, 0, sizeof(h->plane_npix));
+  int rc = 0;
+  do
+  {
+    if ((rc = set_device(h)))
+      break;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess)
+    {
+      rc = fail("cudaGetDeviceProperties failed");
+      break;
+    }
+    if (prop.major < 10)
+    {
+      rc = fail("slicer_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", cfg->device,
+                prop.major, prop.minor);
+      break;
+    }
+    h->sm_count = prop.multiProcessorCount;
+#define TRY(expr)                                                        \
+  if ((expr) != cudaSuccess)                                             \
+  {                                                                      \
+    rc = fail("%s failed: %s", #expr, cudaGetErrorString(cudaGetLastError())); \
+    break;                                                               \
+  }
+    TRY(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
+    TRY(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    TRY(cudaEventCreate(&h->ev_start));
+    TRY(cudaEventCreate(&h->ev_stop));
+    TRY(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
+    TRY(cudaEventCreateWithFlags(&h->ev_pass_done, cudaEventDisableTiming));
+#undef TRY
+    // +64 floats of slack so 16-byte bulk copies may over-read the tail of the last chunk
+    if (cfg->particle_capacity && (rc = dev_alloc(h, &h->d_pos, cfg->particle_capacity * 3 + 64)))
+      break;
+    if (cfg->mass_capacity && (rc = dev_alloc(h, &h->d_mass, cfg->mass_capacity + 64)))
+      break;
+    if ((rc = dev_alloc(h, &h->d_acc, (size_t)cfg->max_planes * h->ntypes_alloc * h->npix2max)))
+      break;
+    if ((rc = dev_alloc(h, &h->d_counts, (size_t)SLICER_MAX_PLANES * SLICER_NTYPES * 2)))
+      break;
+    if ((rc = dev_alloc(h, &h->d_out, h->npix2max)))
+      break;
+    if ((rc = dev_alloc(h, &h->d_sum, h->npix2max)))
+      break;
+    if ((rc = pipelined_init(&h->pipe, h->sm_count)))
+    {
+      rc = fail("pipelined kernel set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    if (cudaMemsetAsync(h->d_acc, 0, (size_t)cfg->max_planes * h->ntypes_alloc * h->npix2max * 8, h->compute) != cudaSuccess ||
+        cudaMemsetAsync(h->d_counts, 0, (size_t)SLICER_MAX_PLANES * SLICER_NTYPES * 2 * 8, h->compute) != cudaSuccess ||
+        cudaStreamSynchronize(h->compute) != cudaSuccess)
+    {
+      rc = fail("initial memset failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+  } while (0);
+  if (rc)
+  {
+    slicer_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+extern "C" void slicer_destroy(slicer_handle *h)
+{
+  if (!h)
+    return;
+  cudaSetDevice(h->cfg.device);
+  if (h->compute)
+    cudaStreamSynchronize(h->compute);
+  if (h->copy)
+    cudaStreamSynchronize(h->copy);
+  if (h->comm && g_nccl.CommDestroy)
+    g_nccl.CommDestroy(h->comm);
+  pipelined_destroy(&h->pipe);
+  cudaFree(h->d_pos);
+  cudaFree(h->d_mass);
+  cudaFree(h->d_acc);
+  cudaFree(h->d_counts);
+  cudaFree(h->d_out);
+  cudaFree(h->d_sum);
+  if (h->ev_start)
+    cudaEventDestroy(h->ev_start);
+  if (h->ev_stop)
+    cudaEventDestroy(h->ev_stop);
+  if (h->ev_copy)
+    cudaEventDestroy(h->ev_copy);
+  if (h->ev_pass_done)
+    cudaEventDestroy(h->ev_pass_done);
+  if (h->compute)
+    cudaStreamDestroy(h->compute);
+  if (h->copy)
+    cudaStreamDestroy(h->copy);
+  delete h;
+}
+
+extern "C" int slicer_frac_bits(slicer_handle *h) { return h ? h->frac_bits : -1; }
+
+// ------------------------------------------------------------------------------------------------------------
+// staging
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int slicer_begin_snapshot(slicer_handle *h, double boxsize, const double massarr[SLICER_NTYPES], int hydro)
+{
+  if (!h)
+    return fail("null handle");
+  if (!(boxsize > 0))
+    return fail("slicer_begin_snapshot: boxsize must be positive");
+  if (set_device(h))
+    return 1;
+  // the pool is about to be overwritten: copies must wait for the pass that still reads it
+  CU(cudaStreamWaitEvent(h->copy, h->ev_pass_done, 0));
+  h->boxsize = boxsize;
+  for (int i = 0; i < SLICER_NTYPES; i++)
+    h->massarr[i] = massarr ? massarr[i] : 0.0;
+  h->hydro = hydro;
+  h->segs.clear();
+  h->pos_used = 0;
+  h->mass_used = 0;
+  return 0;
+}
+
+static bool uses_particle_mass(const slicer_handle *h, int type)
+{
+  return h->hydro && h->massarr[type] == 0; /* densitymaps.cpp:358 */
+}
+
+static int check_stage(slicer_handle *h, int type, int layout)
+{
+  if (!h)
+    return fail("null handle");
+  if (type < 0 || type >= SLICER_NTYPES)
+    return fail("particle type %d out of range", type);
+  if (layout != SLICER_LAYOUT_AOS && layout != SLICER_LAYOUT_SOA)
+    return fail("unknown layout %d", layout);
+  if (!(h->boxsize > 0))
+    return fail("slicer_begin_snapshot must be called before staging");
+  return set_device(h);
+}
+
+// particles are placed at multiples of 4 so every segment starts 16-byte aligned in both layouts
+static size_t pad4(size_t n) { return (n + 3) & ~(size_t)3; }
+
+extern "C" int slicer_stage_particles(slicer_handle *h, int type, const float *pos, int layout, const float *mass, size_t n)
+{
+  if (check_stage(h, type, layout))
+    return 1;
+  if (n == 0)
+    return 0;
+  if (!pos)
+    return fail("slicer_stage_particles: null positions");
+  const bool pm = uses_particle_mass(h, type);
+  if (pm && !mass)
+    return fail("slicer_stage_particles: type %d has massarr==0 in a hydro snapshot: per-particle masses required", type);
+  const size_t npad = pad4(n);
+  if (h->pos_used + npad > h->cfg.particle_capacity)
+    return fail("slicer_stage_particles: %zu particles exceed particle_capacity %zu", h->pos_used + n, h->cfg.particle_capacity);
+  if (pm && h->mass_used + npad > h->cfg.mass_capacity)
+    return fail("slicer_stage_particles: %zu masses exceed mass_capacity %zu", h->mass_used + n, h->cfg.mass_capacity);
+  Segment s;
+  s.type = type;
+  s.n = n;
+  s.layout = layout;
+  s.soa_stride = npad;
+  float *dst = h->d_pos + 3 * h->pos_used;
+  if (layout == SLICER_LAYOUT_AOS)
+    CU(cudaMemcpyAsync(dst, pos, n * 3 * sizeof(float), cudaMemcpyHostToDevice, h->copy));
+  else
+    for (int k = 0; k < 3; k++)
+      CU(cudaMemcpyAsync(dst + k * npad, pos + (size_t)k * n, n * sizeof(float), cudaMemcpyHostToDevice, h->copy));
+  s.dpos = dst;
+  s.dmass = nullptr;
+  if (pm)
+  {
+    float *md = h->d_mass + h->mass_used;
+    CU(cudaMemcpyAsync(md, mass, n * sizeof(float), cudaMemcpyHostToDevice, h->copy));
+    s.dmass = md;
+    h->mass_used += npad;
+  }
+  h->pos_used += npad;
+  h->segs.push_back(s);
+  h->copy_pending = true;
+  return 0;
+}
+
+extern "C" int slicer_stage_device(slicer_handle *h, int type, const void *dev_pos, int layout, const void *dev_mass, size_t n)
+{
+  if (check_stage(h, type, layout))
+    return 1;
+  if (n == 0)
+    return 0;
+  if (!dev_pos)
+    return fail("slicer_stage_device: null positions");
+  if (((uintptr_t)dev_pos & 15) || ((uintptr_t)dev_mass & 15))
+    return fail("slicer_stage_device: device pointers must be 16-byte aligned");
+  if (layout == SLICER_LAYOUT_SOA && (n & 3))
+    return fail("slicer_stage_device: SoA segments need n %% 4 == 0 (rows must stay 16-byte aligned)");
+  const bool pm = uses_particle_mass(h, type);
+  if (pm && !dev_mass)
+    return fail("slicer_stage_device: per-particle masses required for type %d", type);
+  Segment s;
+  s.type = type;
+  s.n = n;
+  s.layout = layout;
+  s.soa_stride = n;
+  s.dpos = (const float *)dev_pos;
+  s.dmass = pm ? (const float *)dev_mass : nullptr;
+  h->segs.push_back(s);
+  return 0;
+}
+
+extern "C" int slicer_stage_synthetic(slicer_handle *h, int type, size_t n, uint64_t seed, int layout)
+{
+  if (check_stage(h, type, layout))
+    return 1;
+  if (n == 0)
+    return 0;
+  if (uses_particle_mass(h, type))
+    return fail("slicer_stage_synthetic: synthetic segments carry no per-particle mass");
+  const size_t npad = pad4(n);
+  if (h->pos_used + npad > h->cfg.particle_capacity)
+    return fail("slicer_stage_synthetic: %zu particles exceed particle_capacity %zu", h->pos_used + n, h->cfg.particle_capacity);
+  Segment s;
+  s.type = type;
+  s.n = n;
+  s.layout = layout;
+  s.soa_stride = npad;
+  float *dst = h->d_pos + 3 * h->pos_used;
+  s.dpos = dst;
+  s.dmass = nullptr;
+  const int blocks = (int)((3 * n + 255) / 256 < (size_t)h->sm_count * 16 ? (3 * n + 255) / 256 : (size_t)h->sm_count * 16);
+  // generated on the copy stream so it orders with other staging work
+  synth_positions_kernel<<<blocks, 256, 0, h->copy>>>(dst, n, npad, layout == SLICER_LAYOUT_SOA, seed, (float)h->boxsize);
+  CU(cudaGetLastError());
+  h->stats.launches++;
+  h->pos_used += npad;
+  h->segs.push_back(s);
+  h->copy_pending = true;
+  return 0;
+}
+
+extern "C" int slicer_download_segment(slicer_handle *h, int segment, float *pos_out, float *mass_out)
+{
+  if (!h)
+    return fail("null handle");
+  if (segment < 0 || segment >= (int)h->segs.size())
+    return fail("segment %d out of range", segment);
+  if (set_device(h))
+    return 1;
+  const Segment &s = h->segs[segment];
+  CU(cudaStreamSynchronize(h->copy));
+  if (pos_out)
+  {
+    if (s.layout == SLICER_LAYOUT_AOS)
+      CU(cudaMemcpy(pos_out, s.dpos, s.n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    else
+      for (int k = 0; k < 3; k++)
+        CU(cudaMemcpy(pos_out + (size_t)k * s.n, s.dpos + k * s.soa_stride, s.n * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  if (mass_out && s.dmass)
+    CU(cudaMemcpy(mass_out, s.dmass, s.n * sizeof(float), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pass set-up
+// ------------------------------------------------------------------------------------------------------------
+static float float_ceil(double d)
+{ // smallest float >= d
+  float f = (float)d;
+  if ((double)f < d)
+    f = nextafterf(f, INFINITY);
+  return f;
+}
+static float float_floor(double d)
+{ // largest float <= d
+  float f = (float)d;
+  if ((double)f > d)
+    f = nextafterf(f, -INFINITY);
+  return f;
+}
+static bool is_f32(double d) { return (double)(float)d == d; }
+
+static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplanes, PassParams *P)
+{
+  if (nplanes < 1 || nplanes > h->cfg.max_planes)
+    return fail("slicer_deposit: nplanes %d outside 1..%d (max_planes)", nplanes, h->cfg.max_planes);
+  memset(P, 0, sizeof(*P));
+  // group planes by randomisation
+  int xf_of[SLICER_MAX_PLANES];
+  int nx = 0;
+  int rep[SLICER_MAX_XFORMS];
+  for (int i = 0; i < nplanes; i++)
+  {
+    const slicer_plane_desc &d = planes[i];
+    if (d.face < 1 || d.face > 6)
+      return fail("plane %d: face %d outside 1..6", i, d.face);
+    for (int k = 0; k < 3; k++)
+      if (d.sgn[k] != 1 && d.sgn[k] != -1)
+        return fail("plane %d: sgn[%d]=%d must be +1 or -1", i, k, d.sgn[k]);
+    if (d.npix < 1 || d.npix > h->cfg.npix_max)
+      return fail("plane %d: npix %d outside 1..%d (npix_max)", i, d.npix, h->cfg.npix_max);
+    if (d.nrepperp < 0)
+      return fail("plane %d: negative nrepperp", i);
+    if (!(d.ld2 > d.ld) || d.ld < 0)
+      return fail("plane %d: need 0 <= ld < ld2", i);
+    if (!(d.fovradiants > 0))
+      return fail("plane %d: fovradiants must be positive", i);
+    int t = -1;
+    for (int j = 0; j < nx && t < 0; j++)
+    {
+      const slicer_plane_desc &r = planes[rep[j]];
+      if (memcmp(r.sgn, d.sgn, sizeof(d.sgn)) == 0 && r.face == d.face && r.centre[0] == d.centre[0] &&
+          r.centre[1] == d.centre[1] && r.centre[2] == d.centre[2] && r.rcase == d.rcase)
+        t = j;
+    }
+    if (t < 0)
+    {
+      if (nx == SLICER_MAX_XFORMS)
+        return fail("slicer_deposit: more than %d distinct randomisations in one pass", SLICER_MAX_XFORMS);
+      rep[nx] = i;
+      t = nx++;
+    }
+    xf_of[i] = t;
+  }
+  P->nxform = nx;
+  P->nplanes = nplanes;
+  static const int perm_of_face[7][3] = {{0, 1, 2}, {0, 1, 2}, {0, 2, 1}, {1, 2, 0}, {1, 0, 2}, {2, 0, 1}, {2, 1, 0}}; /* gadget2io.cpp:223-252 */
+  int slot = 0;
+  for (int t = 0; t < nx; t++)
+  {
+    const slicer_plane_desc &r = planes[rep[t]];
+    XformDev &X = P->xf[t];
+    X.box = h->boxsize;
+    X.boxf = (float)h->boxsize;
+    X.exact_f32 = is_f32(h->boxsize);
+    for (int k = 0; k < 3; k++)
+    {
+      X.c[k] = r.centre[k];
+      X.cf[k] = (float)r.centre[k];
+      X.exact_f32 = X.exact_f32 && is_f32(r.centre[k]);
+      X.perm[k] = perm_of_face[r.face][k];
+      X.sgn[k] = (float)r.sgn[X.perm[k]];
+    }
+    X.rcase = r.rcase;
+    X.first_plane = slot;
+    X.nplanes = 0;
+    X.zmin = INFINITY;
+    X.zmax = -INFINITY;
+    for (int i = 0; i < nplanes; i++)
+    {
+      if (xf_of[i] != t)
+        continue;
+      const slicer_plane_desc &d = planes[i];
+      // NOTE: device slot != caller's plane index; acc/counts pointers keep the caller's index i
+      PlaneDev &L = P->pl[slot++];
+      X.nplanes++;
+      const double minDist = d.ld / h->boxsize * 1.e+3 / POS_U;  /* densitymaps.cpp:346 */
+      const double maxDist = d.ld2 / h->boxsize * 1.e+3 / POS_U; /* densitymaps.cpp:347 */
+      L.zlo = float_ceil(minDist);
+      L.zhi = float_ceil(maxDist);
+      if (L.zlo < X.zmin)
+        X.zmin = L.zlo;
+      if (L.zhi > X.zmax)
+        X.zmax = L.zhi;
+      L.npix = d.npix;
+      L.npixf = (float)d.npix;
+      L.nrep = d.nrepperp;
+      L.pow2 = (d.npix & (d.npix - 1)) == 0;
+      L.T = d.fovradiants * (1. + 2. / d.npix) * 0.5; /* densitymaps.cpp:383 */
+      L.fovrad = d.fovradiants;
+      L.dl = 1. / double(d.npix);  /* utilities.cpp:50 */
+      L.half_dl = 0.5 * L.dl;      /* utilities.cpp:9  */
+      L.onehalf_dl = 0.5 * 3.0 * L.dl; /* utilities.cpp:11 */
+      L.scale = ldexp(1.0, h->frac_bits);
+      if (L.T < 1.5)
+      {
+        const double tt = tan(L.T) * (1.0 + 1e-5);
+        L.pre_ty = float_ceil(tt);
+        L.pre_tx = float_ceil(tt / cos(L.T));
+      }
+      else
+      {
+        L.pre_tx = INFINITY;
+        L.pre_ty = INFINITY;
+      }
+      L.acc = h->d_acc + (size_t)i * h->ntypes_alloc * h->npix2max;
+      L.counts = h->d_counts + (size_t)i * SLICER_NTYPES * 2;
+      L.type_stride = h->cfg.per_type_maps ? h->npix2max : 0;
+      h->plane_npix[i] = d.npix;
+    }
+    // float screen of the pipelined kernel (deposit_pipelined.cuh: screen()); all margins are >= 5x the
+    // worst-case difference between the screen's coordinates and the exact chain's
+    X.tmax = 0.f;
+    for (int q = X.first_plane; q < X.first_plane + X.nplanes; q++)
+      if (P->pl[q].pre_tx > X.tmax)
+        X.tmax = P->pl[q].pre_tx;
+    for (int k = 0; k < 3; k++)
+    {
+      X.sinv[k] = (float)((double)X.sgn[k] / h->boxsize);
+      X.offs[k] = (float)((X.sgn[k] < 0.f ? 1.0 : 0.0) - X.c[k]);
+    }
+    const float zulp = nextafterf(X.zmax, INFINITY) - X.zmax;
+    const float mz = 2e-6f + 4.f * zulp;
+    X.zlo_m = X.zmin - mz;
+    X.zhi_m = X.zmax + mz;
+    X.zamb = 0.5f - 2e-6f;
+    X.thr_m = isinf(X.tmax) ? 0.f : 4e-6f + X.tmax * mz * 1.01f;
+    X.raw_half = (float)(0.5 * h->boxsize);
+    X.raw_amb = (float)(h->boxsize * (0.5 - 4e-6));
+  }
+  return 0;
+}
+
+static void fill_segment(const slicer_handle *h, const Segment &s, SegmentDev *D)
+{
+  D->pos = s.dpos;
+  D->mass = s.dmass;
+  D->n = s.n;
+  D->soa_stride = s.soa_stride;
+  D->const_mass = (float)h->massarr[s.type]; /* densitymaps.cpp:372: num_float1 = data.massarr[i] */
+  D->max_m = float_floor(h->cfg.max_m);      /* float m > double MAX_M  <=>  m > largest float <= MAX_M */
+  D->type = s.type;
+  D->layout = s.layout;
+}
+
+static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplanes, bool accumulate)
+{
+  if (!h || !planes)
+    return fail("slicer_deposit: null argument");
+  if (set_device(h))
+    return 1;
+  PassParams P;
+  if (build_pass(h, planes, nplanes, &P))
+    return 1;
+  if (h->copy_pending)
+  {
+    CU(cudaEventRecord(h->ev_copy, h->copy));
+    CU(cudaStreamWaitEvent(h->compute, h->ev_copy, 0));
+    h->copy_pending = false;
+  }
+  if (!accumulate)
+  {
+    CU(cudaMemsetAsync(h->d_acc, 0, (size_t)nplanes * h->ntypes_alloc * h->npix2max * sizeof(unsigned long long), h->compute));
+    CU(cudaMemsetAsync(h->d_counts, 0, (size_t)nplanes * SLICER_NTYPES * 2 * sizeof(unsigned long long), h->compute));
+  }
+  int kernel = h->cfg.kernel;
+  if (kernel == SLICER_KERNEL_AUTO)
+    kernel = SLICER_KERNEL_PIPELINED;
+  CU(cudaEventRecord(h->ev_start, h->compute));
+  for (size_t si = 0; si < h->segs.size(); si++)
+  {
+    SegmentDev D;
+    fill_segment(h, h->segs[si], &D);
+    if (D.n == 0)
+      continue;
+    if (kernel == SLICER_KERNEL_PIPELINED)
+    {
+      if (pipelined_launch(&h->pipe, h->cfg.mas, P, D, h->compute))
+        return fail("pipelined launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    else
+    {
+      size_t want = (D.n + 255) / 256;
+      size_t cap = (size_t)h->sm_count * 8;
+      int blocks = (int)(want < cap ? want : cap);
+      if (h->cfg.mas == SLICER_MAS_NGP)
+        deposit_simple_kernel<SLICER_MAS_NGP><<<blocks, 256, 0, h->compute>>>(P, D);
+      else
+        deposit_simple_kernel<SLICER_MAS_TSC><<<blocks, 256, 0, h->compute>>>(P, D);
+      CU(cudaGetLastError());
+    }
+    h->stats.launches++;
+    h->stats.particles_streamed += D.n;
+  }
+  CU(cudaEventRecord(h->ev_stop, h->compute));
+  CU(cudaEventRecord(h->ev_pass_done, h->compute));
+  h->have_timing = true;
+  return 0;
+}
+
+extern "C" int slicer_deposit(slicer_handle *h, const slicer_plane_desc *planes, int nplanes)
+{
+  return run_pass(h, planes, nplanes, false);
+}
+
+extern "C" int slicer_deposit_accumulate(slicer_handle *h, const slicer_plane_desc *planes, int nplanes)
+{
+  return run_pass(h, planes, nplanes, true);
+}
+
+extern "C" int slicer_synchronize(slicer_handle *h)
+{
+  if (!h)
+    return fail("null handle");
+  if (set_device(h))
+    return 1;
+  CU(cudaStreamSynchronize(h->copy));
+  CU(cudaStreamSynchronize(h->compute));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// read-out
+// ------------------------------------------------------------------------------------------------------------
+static int check_plane(slicer_handle *h, int plane, int type)
+{
+  if (!h)
+    return fail("null handle");
+  if (plane < 0 || plane >= h->cfg.max_planes)
+    return fail("plane %d outside 0..%d", plane, h->cfg.max_planes - 1);
+  if (h->plane_npix[plane] <= 0)
+    return fail("plane %d has not been deposited", plane);
+  if (type < -1 || type >= SLICER_NTYPES)
+    return fail("type %d outside -1..5", type);
+  if (type >= 0 && !h->cfg.per_type_maps)
+    return fail("per-type maps were not requested (slicer_config.per_type_maps)");
+  return set_device(h);
+}
+
+extern "C" int slicer_fetch(slicer_handle *h, int plane, int type, float *out_map, long long counts[SLICER_NTYPES],
+                            long long ingrid[SLICER_NTYPES])
+{
+  if (check_plane(h, plane, type))
+    return 1;
+  const size_t npix2 = (size_t)h->plane_npix[plane] * h->plane_npix[plane];
+  const unsigned long long *base = h->d_acc + (size_t)plane * h->ntypes_alloc * h->npix2max;
+  if (out_map)
+  {
+    const unsigned long long *src = type >= 0 ? base + (size_t)type * h->npix2max : base;
+    const int nt = type >= 0 ? 1 : h->ntypes_alloc;
+    const int blocks = (int)((npix2 + 255) / 256 < (size_t)h->sm_count * 8 ? (npix2 + 255) / 256 : (size_t)h->sm_count * 8);
+    finalize_map_kernel<<<blocks, 256, 0, h->compute>>>(src, h->npix2max, nt, npix2, ldexp(1.0, -h->frac_bits), h->d_out);
+    CU(cudaGetLastError());
+    h->stats.launches++;
+    CU(cudaMemcpyAsync(out_map, h->d_out, npix2 * sizeof(float), cudaMemcpyDeviceToHost, h->compute));
+  }
+  unsigned long long c[SLICER_NTYPES * 2];
+  CU(cudaMemcpyAsync(c, h->d_counts + (size_t)plane * SLICER_NTYPES * 2, sizeof(c), cudaMemcpyDeviceToHost, h->compute));
+  CU(cudaStreamSynchronize(h->compute));
+  for (int t = 0; t < SLICER_NTYPES; t++)
+  {
+    if (counts)
+      counts[t] = (long long)c[2 * t];
+    if (ingrid)
+      ingrid[t] = (long long)c[2 * t + 1];
+  }
+  return 0;
+}
+
+extern "C" int slicer_fetch_fixed(slicer_handle *h, int plane, int type, long long *out)
+{
+  if (check_plane(h, plane, type))
+    return 1;
+  if (!out)
+    return fail("slicer_fetch_fixed: null output");
+  const size_t npix2 = (size_t)h->plane_npix[plane] * h->plane_npix[plane];
+  const unsigned long long *base = h->d_acc + (size_t)plane * h->ntypes_alloc * h->npix2max;
+  const unsigned long long *src = type >= 0 ? base + (size_t)type * h->npix2max : base;
+  const int nt = type >= 0 ? 1 : h->ntypes_alloc;
+  const int blocks = (int)((npix2 + 255) / 256 < (size_t)h->sm_count * 8 ? (npix2 + 255) / 256 : (size_t)h->sm_count * 8);
+  sum_types_kernel<<<blocks, 256, 0, h->compute>>>(src, h->npix2max, nt, npix2, h->d_sum);
+  CU(cudaGetLastError());
+  h->stats.launches++;
+  CU(cudaMemcpyAsync(out, h->d_sum, npix2 * sizeof(long long), cudaMemcpyDeviceToHost, h->compute));
+  CU(cudaStreamSynchronize(h->compute));
+  return 0;
+}
+
+extern "C" int slicer_get_stats(slicer_handle *h, slicer_stats *out)
+{
+  if (!h || !out)
+    return fail("null argument");
+  if (set_device(h))
+    return 1;
+  if (h->have_timing)
+  {
+    CU(cudaEventSynchronize(h->ev_stop));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop));
+    h->stats.last_deposit_ms = ms;
+  }
+  size_t res = 0;
+  for (size_t i = 0; i < h->segs.size(); i++)
+    res += h->segs[i].n;
+  h->stats.resident_particles = res;
+  h->stats.device_bytes = h->device_bytes;
+  h->stats.sm_count = h->sm_count;
+  *out = h->stats;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// multi-GPU: ncclReduce(int64, sum) of the plane accumulators — replaces slicer-v2.cpp:214-217
+// ------------------------------------------------------------------------------------------------------------
+extern "C" int slicer_comm_unique_id(char id[128])
+{
+  if (load_nccl())
+    return 1;
+  ncclUniqueId u;
+  NC(g_nccl.GetUniqueId(&u));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(id, &u, 128);
+  return 0;
+}
+
+extern "C" int slicer_comm_init_rank(slicer_handle *h, const char id[128], int nranks, int rank)
+{
+  if (!h)
+    return fail("null handle");
+  if (load_nccl() || set_device(h))
+    return 1;
+  if (h->comm)
+    return fail("communicator already initialised");
+  ncclUniqueId u;
+  memcpy(&u, id, 128);
+  NC(g_nccl.CommInitRank(&h->comm, nranks, u, rank));
+  h->nranks = nranks;
+  h->rank = rank;
+  return 0;
+}
+
+extern "C" int slicer_comm_init_all(slicer_handle **handles, int n)
+{
+  if (!handles || n < 1)
+    return fail("slicer_comm_init_all: bad arguments");
+  if (load_nccl())
+    return 1;
+  std::vector<int> devs(n);
+  std::vector<ncclComm_t> comms(n);
+  for (int i = 0; i < n; i++)
+  {
+    if (!handles[i] || handles[i]->comm)
+      return fail("slicer_comm_init_all: handle %d null or already in a communicator", i);
+    devs[i] = handles[i]->cfg.device;
+  }
+  NC(g_nccl.CommInitAll(comms.data(), n, devs.data()));
+  for (int i = 0; i < n; i++)
+  {
+    handles[i]->comm = comms[i];
+    handles[i]->nranks = n;
+    handles[i]->rank = i;
+  }
+  return 0;
+}
+
+static int enqueue_reduce(slicer_handle *h, int nplanes, int root)
+{
+  const size_t count = (size_t)nplanes * h->ntypes_alloc * h->npix2max;
+  NC(g_nccl.Reduce(h->d_acc, h->d_acc, count, ncclInt64, ncclSum, root, h->comm, h->compute));
+  NC(g_nccl.Reduce(h->d_counts, h->d_counts, (size_t)nplanes * SLICER_NTYPES * 2, ncclUint64, ncclSum, root, h->comm, h->compute));
+  return 0;
+}
+
+extern "C" int slicer_reduce(slicer_handle *h, int nplanes, int root)
+{
+  if (!h)
+    return fail("null handle");
+  if (!h->comm || h->nranks == 1)
+    return 0;
+  if (nplanes < 1 || nplanes > h->cfg.max_planes)
+    return fail("slicer_reduce: nplanes %d outside 1..%d", nplanes, h->cfg.max_planes);
+  if (set_device(h))
+    return 1;
+  NC(g_nccl.GroupStart());
+  int rc = enqueue_reduce(h, nplanes, root);
+  NC(g_nccl.GroupEnd());
+  return rc;
+}
+
+extern "C" int slicer_reduce_all(slicer_handle **handles, int n, int nplanes, int root)
+{
+  if (!handles || n < 1)
+    return fail("slicer_reduce_all: bad arguments");
+  if (n == 1)
+    return 0;
+  if (load_nccl())
+    return 1;
+  NC(g_nccl.GroupStart());
+  int rc = 0;
+  for (int i = 0; i < n && !rc; i++)
+  {
+    if (cudaSetDevice(handles[i]->cfg.device) != cudaSuccess)
+      rc = fail("cudaSetDevice failed");
+    else
+      rc = enqueue_reduce(handles[i], nplanes, root);
+  }
+  NC(g_nccl.GroupEnd());
+  return rc;
+}

@@ -147,3 +147,20 @@ def clustered_positions(n: int, boxsize: float, seed: int, nclumps: int = 64, si
     p = np.mod(p, boxsize).astype(np.float32)
     p[p >= np.float32(boxsize)] = 0.0
     return p
+
+
+_M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def hash_positions(n: int, boxsize: float, seed: int, start: int = 0) -> np.ndarray:
+    """Host restatement of the device generator (csrc/aux_kernels.cuh: synth_mix / synth_positions_kernel):
+    coordinate k of particle i = float(splitmix64(seed, 3 i + k) >> 40) * 2^-24 * float(boxsize).
+    Any chunk [start, start+n) can be regenerated without storing the snapshot."""
+    idx = (np.arange(start * 3, (start + n) * 3, dtype=np.uint64) + np.uint64(1))
+    with np.errstate(over="ignore"):
+        z = np.uint64(seed & 0xFFFFFFFFFFFFFFFF) + idx * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    return (u * np.float32(boxsize)).astype(np.float32).reshape(n, 3)

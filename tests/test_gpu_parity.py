@@ -1,0 +1,195 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle.  All tests need a B200.
+
+Bars (BASELINE.json north_star): NGP pixel indices and per-plane/type accepted counts bit-exact; TSC per-pixel
+mass within 1e-6 relative (plus an absolute floor of 1e-9 * particle mass: contributions go down to 1e-12 m);
+total mass conserved to 1e-12 against the exact (double) sum of the same float contributions.  On top of that
+the int64 fixed-point accumulators are compared bit for bit with the oracle's (orc_gridist_w_fixed): they are
+order independent, so anything but equality is a real difference in some particle's arithmetic.
+"""
+import numpy as np
+import pytest
+
+from slicer_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [capi.KERNEL_SIMPLE, capi.KERNEL_PIPELINED]
+NAMES = ["dm_face1", "dm_face3_pile2", "dm_face4_repl", "hydro_multi", "odd_box_face2", "face5_repl2"]
+
+
+def stage_types(s, types, layout=capi.LAYOUT_AOS):
+    for t in types:
+        pos = t["raw"] if layout == capi.LAYOUT_AOS else np.ascontiguousarray(t["raw"].T)
+        s.stage(t["type"], pos, t.get("masses"), layout=layout)
+
+
+def run_plane(types, plane, npix, mas, kernel, layout=capi.LAYOUT_AOS, massarr=None, hydro=False, per_type=True):
+    n = sum(len(t["raw"]) for t in types) + 64
+    with capi.Slicer(npix_max=npix, max_planes=1, mas=mas, particle_capacity=n, mass_capacity=n, per_type_maps=per_type,
+                     kernel=kernel) as s:
+        s.begin_snapshot(plane["boxsize"], massarr, hydro)
+        stage_types(s, types, layout)
+        d = capi.plane_desc(plane["sgn"], plane["face"], plane["centre"], plane["rcase"], plane["ld"], plane["ld2"],
+                            plane["fovradiants"], npix, plane.get("nrepperp", 0))
+        s.deposit([d])
+        out = {}
+        _, counts, ingrid = s.fetch(0, -1, npix, want_map=False)
+        out["counts"], out["ingrid"] = counts, ingrid
+        out["maps"] = {}
+        out["fixed"] = {}
+        for t in types:
+            ty = t["type"]
+            out["maps"][ty] = s.fetch(0, ty, npix)[0].reshape(-1)
+            out["fixed"][ty] = s.fetch_fixed(0, ty, npix).reshape(-1)
+        out["total"] = s.fetch(0, -1, npix)[0].reshape(-1)
+        out["frac_bits"] = s.frac_bits
+        return out
+
+
+def check_against_oracle(oracle, types, plane, npix, got, do_ngp, mass_scale):
+    res = oracle.plane_from_particles(types, plane, npix, do_ngp=do_ngp, frac_bits=got["frac_bits"])
+    assert got["counts"].tolist() == res["counts"].tolist()
+    assert got["ingrid"].tolist() == res["ingrid"].tolist()
+    for t in types:
+        ty = t["type"]
+        # int64 fixed point: bit exact
+        assert np.array_equal(got["fixed"][ty], res["fixed"][ty]), f"type {ty}: fixed-point accumulators differ"
+        # float map vs the reference's float32-in-order map: 1e-6 relative + floor
+        np.testing.assert_allclose(got["maps"][ty], res["maps"][ty], rtol=1e-6, atol=1e-9 * mass_scale)
+        # mass conservation against the exact sum of the same contributions
+        tot = res["f64"][ty].sum()
+        if tot > 0:
+            assert abs(got["fixed"][ty].sum() * 2.0 ** -got["frac_bits"] - tot) <= 1e-12 * tot
+    if do_ngp:
+        # NGP pixel indices: the set of hit pixels and the number of hits per pixel (constant-mass types)
+        for t in types:
+            if "const_mass" in t and t["const_mass"] > 0:
+                ty = t["type"]
+                xs, ys, _ = res["accepted"][ty]
+                cells = oracle.ngp_cells_fast(xs, ys, npix)
+                hist = np.bincount(cells[cells >= 0], minlength=npix * npix)
+                q = int(np.rint(float(np.float32(t["const_mass"])) * 2.0 ** got["frac_bits"]))
+                assert np.array_equal(got["fixed"][ty], hist * q)
+    return res
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("mas", [capi.MAS_TSC, capi.MAS_NGP])
+@pytest.mark.parametrize("name", NAMES)
+def test_golden_cases(oracle, golden, name, mas, kernel):
+    m = golden.meta[name]
+    types, plane = golden.types(name), golden.plane(name)
+    got = run_plane(types, plane, m["npix"], mas, kernel, massarr=m["massarr"], hydro=bool(m["hydro"]))
+    assert got["counts"].tolist() == m["counts"]  # the reference's own mapParticles counts
+    check_against_oracle(oracle, types, plane, m["npix"], got, mas == capi.MAS_NGP, 1.0)
+    tag = "ngp" if mas == capi.MAS_NGP else "tsc"
+    for t in m["types_with_maps"]:  # the reference's own float maps
+        np.testing.assert_allclose(got["maps"][t], golden.arr[f"{name}/{tag}{t}"].reshape(-1), rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("layout", [capi.LAYOUT_AOS, capi.LAYOUT_SOA])
+@pytest.mark.parametrize("n", [0, 1, 3, 1023, 1024, 1025, 4099, 300001])
+def test_ragged_sizes(oracle, n, layout):
+    """Empty, sub-chunk, exact-chunk and ragged segment sizes (the TMA ring + plain-load tail)."""
+    box = 128000.0
+    pos = synth.uniform_positions(max(n, 1), box, 77)[:n]
+    types = [dict(type=1, raw=pos, const_mass=1.0375)]
+    plane = dict(boxsize=box, sgn=[1, -1, 1], face=2, centre=[0.25, 0.5, 0.125], rcase=1.0, ld=128.0 + 32, ld2=128.0 + 64,
+                 nrepperp=0, fovradiants=0.5)
+    for mas in (capi.MAS_TSC, capi.MAS_NGP):
+        got = run_plane(types, plane, 128, mas, capi.KERNEL_PIPELINED, layout=layout, massarr=[0, 1.0375, 0, 0, 0, 0])
+        check_against_oracle(oracle, types, plane, 128, got, mas == capi.MAS_NGP, 1.0)
+
+
+def test_multi_plane_pass_matches_single_planes(oracle):
+    """One pass over 9 planes from 3 randomisations == 9 single-plane passes == oracle (C1-like geometry)."""
+    box = 128000.0
+    n = 400000
+    pos = synth.uniform_positions(n, box, 5)
+    types = [dict(type=1, raw=pos, const_mass=1.0375)]
+    rnd = oracle.randomize_box(-229, -230, -231, [1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0])
+    fov = float(np.float32(8.0)) / 180.0 * np.pi
+    npix = 256
+    planes = []
+    for i in range(3, 12):
+        planes.append(dict(boxsize=box, sgn=[rnd["sgnX"][i], rnd["sgnY"][i], rnd["sgnZ"][i]], face=rnd["face"][i],
+                           centre=[rnd["x0"][i], rnd["y0"][i], rnd["z0"][i]], rcase=float(i // 4), ld=32.0 * i, ld2=32.0 * (i + 1),
+                           nrepperp=0, fovradiants=fov))
+    with capi.Slicer(npix_max=npix, max_planes=9, mas=capi.MAS_TSC, particle_capacity=n + 64) as s:
+        s.begin_snapshot(box, [0, 1.0375, 0, 0, 0, 0], False)
+        s.stage(1, pos)
+        s.deposit([capi.plane_desc(p["sgn"], p["face"], p["centre"], p["rcase"], p["ld"], p["ld2"], fov, npix) for p in planes])
+        fb = s.frac_bits
+        for k, p in enumerate(planes):
+            res = oracle.plane_from_particles(types, p, npix, frac_bits=fb)
+            _, counts, ingrid = s.fetch(k, -1, npix, want_map=False)
+            assert counts.tolist() == res["counts"].tolist()
+            assert np.array_equal(s.fetch_fixed(k, -1, npix).reshape(-1), res["fixed"][1])
+            assert counts[1] > 50
+
+
+def test_clustered_particles_contention(oracle):
+    """Strongly clustered positions: many deposits into few pixels (atomic contention) stay exact."""
+    box = 64000.0
+    n = 200000
+    pos = synth.clustered_positions(n, box, 9, nclumps=6, sigma_frac=0.002)
+    types = [dict(type=1, raw=pos, const_mass=0.5)]
+    plane = dict(boxsize=box, sgn=[1, 1, 1], face=1, centre=[0.0, 0.0, 0.0], rcase=0.0, ld=0.0, ld2=64.0, nrepperp=0,
+                 fovradiants=1.2)
+    got = run_plane(types, plane, 64, capi.MAS_TSC, capi.KERNEL_PIPELINED, massarr=[0, 0.5, 0, 0, 0, 0])
+    check_against_oracle(oracle, types, plane, 64, got, False, 0.5)
+
+
+def test_accumulate_over_subfiles(oracle):
+    """deposit + deposit_accumulate over two batches == one pass over both (createDensityMaps' sub-file loop)."""
+    box = 100000.0
+    a = synth.uniform_positions(50000, box, 1)
+    b = synth.uniform_positions(70001, box, 2)
+    plane = dict(boxsize=box, sgn=[-1, 1, -1], face=5, centre=[0.3, 0.6, 0.9], rcase=0.0, ld=25.0, ld2=50.0, nrepperp=0,
+                 fovradiants=0.9)
+    d = capi.plane_desc(plane["sgn"], plane["face"], plane["centre"], 0.0, 25.0, 50.0, 0.9, 100)
+    with capi.Slicer(npix_max=100, max_planes=1, particle_capacity=80000) as s:
+        s.begin_snapshot(box, [0, 2.0, 0, 0, 0, 0], False)
+        s.stage(1, a)
+        s.deposit([d])
+        s.begin_snapshot(box, [0, 2.0, 0, 0, 0, 0], False)
+        s.stage(1, b)
+        s.deposit([d], accumulate=True)
+        fixed = s.fetch_fixed(0, -1, 100).reshape(-1)
+        fb = s.frac_bits
+        _, counts, _ = s.fetch(0, -1, 100, want_map=False)
+    res = oracle.plane_from_particles([dict(type=1, raw=np.concatenate([a, b]), const_mass=2.0)], plane, 100, frac_bits=fb)
+    assert counts.tolist() == res["counts"].tolist()
+    assert np.array_equal(fixed, res["fixed"][1])
+
+
+def test_synthetic_generator_matches_host(oracle):
+    """slicer_stage_synthetic (device) == slicer_b200.synth.hash_positions (host), and deposits agree with the oracle."""
+    box = 256000.0
+    n = 123457
+    for layout in (capi.LAYOUT_AOS, capi.LAYOUT_SOA):
+        with capi.Slicer(npix_max=64, max_planes=1, particle_capacity=n + 8) as s:
+            s.begin_snapshot(box, [0, 1.0, 0, 0, 0, 0], False)
+            s.stage_synthetic(1, n, 42, layout=layout)
+            dev = s.download_segment(0, n, layout=layout)
+        host = synth.hash_positions(n, box, 42)
+        if layout == capi.LAYOUT_SOA:
+            dev = dev.T
+        assert np.array_equal(dev.view(np.uint32), host.view(np.uint32))
+
+
+def test_errors_are_loud():
+    with capi.Slicer(npix_max=32, max_planes=2, particle_capacity=10) as s:
+        with pytest.raises(capi.SlicerError):
+            s.stage(1, np.zeros((4, 3), np.float32))  # begin_snapshot not called
+        s.begin_snapshot(1000.0, [0, 1, 0, 0, 0, 0], False)
+        with pytest.raises(capi.SlicerError):
+            s.stage(1, np.zeros((100, 3), np.float32))  # over capacity
+        with pytest.raises(capi.SlicerError):
+            s.deposit([capi.plane_desc([1, 1, 1], 7, [0, 0, 0], 0, 0, 1, 0.1, 32)])  # bad face
+        with pytest.raises(capi.SlicerError):
+            s.deposit([capi.plane_desc([1, 1, 1], 1, [0, 0, 0], 0, 0, 1, 0.1, 64)])  # npix > npix_max
+        with pytest.raises(capi.SlicerError):
+            s.fetch(0, 3, 32)  # per-type maps not requested
+    with pytest.raises(capi.SlicerError):
+        capi.Slicer(npix_max=32, max_planes=99)
