@@ -39,6 +39,7 @@ class Config(C.Structure):
         ("particle_capacity", C.c_size_t),
         ("mass_capacity", C.c_size_t),
         ("kernel", C.c_int),
+        ("staging_buffers", C.c_int),
     ]
 
 
@@ -66,16 +67,19 @@ class Stats(C.Structure):
         ("resident_particles", C.c_size_t),
         ("device_bytes", C.c_size_t),
         ("sm_count", C.c_int),
+        ("deposit_ms_sum", C.c_double),
+        ("deposit_passes", C.c_ulonglong),
+        ("deposit_launches", C.c_ulonglong),
     ]
 
 
 EXPORTS = [
     "slicer_last_error", "slicer_device_count", "slicer_create", "slicer_destroy", "slicer_alloc_pinned",
-    "slicer_free_pinned", "slicer_begin_snapshot", "slicer_stage_particles", "slicer_stage_device",
+    "slicer_free_pinned", "slicer_begin_snapshot", "slicer_next_batch", "slicer_stage_particles", "slicer_stage_device",
     "slicer_stage_synthetic", "slicer_download_segment", "slicer_deposit", "slicer_deposit_accumulate",
     "slicer_reduce", "slicer_fetch", "slicer_fetch_fixed", "slicer_synchronize", "slicer_get_stats",
     "slicer_frac_bits", "slicer_comm_unique_id", "slicer_comm_init_rank", "slicer_comm_init_all",
-    "slicer_reduce_all",
+    "slicer_reduce_all", "slicer_reset_stats", "slicer_timer_begin", "slicer_timer_end",
 ]
 
 
@@ -107,6 +111,10 @@ def lib() -> C.CDLL:
     L.slicer_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.slicer_free_pinned.argtypes = [C.c_void_p]
     L.slicer_begin_snapshot.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double), C.c_int]
+    L.slicer_next_batch.argtypes = [C.c_void_p]
+    L.slicer_reset_stats.argtypes = [C.c_void_p]
+    L.slicer_timer_begin.argtypes = [C.c_void_p]
+    L.slicer_timer_end.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.slicer_stage_particles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.slicer_stage_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.slicer_stage_synthetic.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_uint64, C.c_int]
@@ -183,10 +191,10 @@ class Slicer:
 
     def __init__(self, npix_max: int, max_planes: int = 4, mas: int = MAS_TSC, particle_capacity: int = 0,
                  mass_capacity: int = 0, per_type_maps: bool = False, device: int = 0, kernel: int = KERNEL_AUTO,
-                 frac_bits: int = 0, max_m: float = 1e3):
+                 frac_bits: int = 0, max_m: float = 1e3, staging_buffers: int = 1):
         cfg = Config(device=device, mas=mas, max_m=max_m, frac_bits=frac_bits, max_planes=max_planes,
                      npix_max=npix_max, per_type_maps=int(per_type_maps), particle_capacity=particle_capacity,
-                     mass_capacity=mass_capacity, kernel=kernel)
+                     mass_capacity=mass_capacity, kernel=kernel, staging_buffers=staging_buffers)
         h = C.c_void_p()
         _check(lib().slicer_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -220,6 +228,9 @@ class Slicer:
         arr = (C.c_double * 6)(*[float(v) for v in massarr])
         _check(lib().slicer_begin_snapshot(self.h, float(boxsize), arr, int(hydro)))
         self._keep.clear()
+
+    def next_batch(self):
+        _check(lib().slicer_next_batch(self.h))
 
     def stage(self, ptype: int, pos: np.ndarray, mass: Optional[np.ndarray] = None, layout: int = LAYOUT_AOS):
         """pos: float32 [n,3] (AoS) or [3,n] (SoA); mass: float32 [n] or None."""
@@ -288,6 +299,17 @@ class Slicer:
         out = np.empty(npix * npix, np.int64)
         _check(lib().slicer_fetch_fixed(self.h, plane, ptype, out.ctypes.data))
         return out.reshape(npix, npix)
+
+    def reset_stats(self):
+        _check(lib().slicer_reset_stats(self.h))
+
+    def timer_begin(self):
+        _check(lib().slicer_timer_begin(self.h))
+
+    def timer_end(self) -> float:
+        ms = C.c_double()
+        _check(lib().slicer_timer_end(self.h, C.byref(ms)))
+        return ms.value
 
     def stats(self) -> Stats:
         st = Stats()

@@ -97,6 +97,8 @@ static int load_nccl()
 // ------------------------------------------------------------------------------------------------------------
 // handle
 // ------------------------------------------------------------------------------------------------------------
+static const size_t PASS_RING = 256; // pending (start, stop) event pairs kept per handle
+
 struct Segment
 {
   int type;
@@ -115,9 +117,16 @@ struct slicer_handle
   size_t npix2max;
   int sm_count;
   cudaStream_t compute = nullptr, copy = nullptr;
-  cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_copy = nullptr, ev_pass_done = nullptr;
-  float *d_pos = nullptr;  // particle_capacity * 3 floats (+pad)
-  float *d_mass = nullptr; // mass_capacity floats (+pad)
+  cudaEvent_t ev_copy = nullptr;
+  cudaEvent_t ev_buf_done[2] = {nullptr, nullptr}; // last pass that read staging pool b
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;    // slicer_timer_*
+  std::vector<cudaEvent_t> pass_ev;                // ring of (start, stop) pairs, resolved lazily
+  size_t pass_head = 0, pass_tail = 0;             // pairs [tail, head) are pending
+  int nbuf = 1, cur_buf = 0;
+  float *d_pos_pool = nullptr;  // nbuf * (particle_capacity * 3 + 64) floats
+  float *d_mass_pool = nullptr; // nbuf * (mass_capacity + 64) floats
+  float *d_pos = nullptr;  // current pool
+  float *d_mass = nullptr;
   size_t pos_used = 0;     // in particles
   size_t mass_used = 0;
   std::vector<Segment> segs;
@@ -129,7 +138,6 @@ struct slicer_handle
   double massarr[SLICER_NTYPES] = {0, 0, 0, 0, 0, 0};
   int hydro = 0;
   int plane_npix[SLICER_MAX_PLANES];
-  bool have_timing = false;
   bool copy_pending = false;
   slicer_stats stats;
   size_t device_bytes = 0;
@@ -228,16 +236,31 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
   }
     TRY(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
     TRY(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
-    TRY(cudaEventCreate(&h->ev_start));
-    TRY(cudaEventCreate(&h->ev_stop));
     TRY(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
-    TRY(cudaEventCreateWithFlags(&h->ev_pass_done, cudaEventDisableTiming));
+    TRY(cudaEventCreateWithFlags(&h->ev_buf_done[0], cudaEventDisableTiming));
+    TRY(cudaEventCreateWithFlags(&h->ev_buf_done[1], cudaEventDisableTiming));
+    TRY(cudaEventCreate(&h->ev_t0));
+    TRY(cudaEventCreate(&h->ev_t1));
+    h->pass_ev.resize(2 * PASS_RING, nullptr);
+    {
+      bool bad = false;
+      for (size_t i = 0; i < h->pass_ev.size() && !bad; i++)
+        bad = cudaEventCreate(&h->pass_ev[i]) != cudaSuccess;
+      if (bad)
+      {
+        rc = fail("cudaEventCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+        break;
+      }
+    }
 #undef TRY
+    h->nbuf = cfg->staging_buffers >= 2 ? 2 : 1;
     // +64 floats of slack so 16-byte bulk copies may over-read the tail of the last chunk
-    if (cfg->particle_capacity && (rc = dev_alloc(h, &h->d_pos, cfg->particle_capacity * 3 + 64)))
+    if (cfg->particle_capacity && (rc = dev_alloc(h, &h->d_pos_pool, h->nbuf * (cfg->particle_capacity * 3 + 64))))
       break;
-    if (cfg->mass_capacity && (rc = dev_alloc(h, &h->d_mass, cfg->mass_capacity + 64)))
+    if (cfg->mass_capacity && (rc = dev_alloc(h, &h->d_mass_pool, h->nbuf * (cfg->mass_capacity + 64))))
       break;
+    h->d_pos = h->d_pos_pool;
+    h->d_mass = h->d_mass_pool;
     if ((rc = dev_alloc(h, &h->d_acc, (size_t)cfg->max_planes * h->ntypes_alloc * h->npix2max)))
       break;
     if ((rc = dev_alloc(h, &h->d_counts, (size_t)SLICER_MAX_PLANES * SLICER_NTYPES * 2)))
@@ -280,20 +303,24 @@ extern "C" void slicer_destroy(slicer_handle *h)
   if (h->comm && g_nccl.CommDestroy)
     g_nccl.CommDestroy(h->comm);
   pipelined_destroy(&h->pipe);
-  cudaFree(h->d_pos);
-  cudaFree(h->d_mass);
+  cudaFree(h->d_pos_pool);
+  cudaFree(h->d_mass_pool);
   cudaFree(h->d_acc);
   cudaFree(h->d_counts);
   cudaFree(h->d_out);
   cudaFree(h->d_sum);
-  if (h->ev_start)
-    cudaEventDestroy(h->ev_start);
-  if (h->ev_stop)
-    cudaEventDestroy(h->ev_stop);
   if (h->ev_copy)
     cudaEventDestroy(h->ev_copy);
-  if (h->ev_pass_done)
-    cudaEventDestroy(h->ev_pass_done);
+  for (int b = 0; b < 2; b++)
+    if (h->ev_buf_done[b])
+      cudaEventDestroy(h->ev_buf_done[b]);
+  if (h->ev_t0)
+    cudaEventDestroy(h->ev_t0);
+  if (h->ev_t1)
+    cudaEventDestroy(h->ev_t1);
+  for (size_t i = 0; i < h->pass_ev.size(); i++)
+    if (h->pass_ev[i])
+      cudaEventDestroy(h->pass_ev[i]);
   if (h->compute)
     cudaStreamDestroy(h->compute);
   if (h->copy)
@@ -314,12 +341,26 @@ extern "C" int slicer_begin_snapshot(slicer_handle *h, double boxsize, const dou
     return fail("slicer_begin_snapshot: boxsize must be positive");
   if (set_device(h))
     return 1;
-  // the pool is about to be overwritten: copies must wait for the pass that still reads it
-  CU(cudaStreamWaitEvent(h->copy, h->ev_pass_done, 0));
   h->boxsize = boxsize;
   for (int i = 0; i < SLICER_NTYPES; i++)
     h->massarr[i] = massarr ? massarr[i] : 0.0;
   h->hydro = hydro;
+  return slicer_next_batch(h);
+}
+
+extern "C" int slicer_next_batch(slicer_handle *h)
+{
+  if (!h)
+    return fail("null handle");
+  if (!(h->boxsize > 0))
+    return fail("slicer_begin_snapshot must be called before slicer_next_batch");
+  if (set_device(h))
+    return 1;
+  h->cur_buf = (h->cur_buf + 1) % h->nbuf;
+  // this pool is about to be overwritten: copies must wait for the pass that last read it
+  CU(cudaStreamWaitEvent(h->copy, h->ev_buf_done[h->cur_buf], 0));
+  h->d_pos = h->d_pos_pool ? h->d_pos_pool + (size_t)h->cur_buf * (h->cfg.particle_capacity * 3 + 64) : nullptr;
+  h->d_mass = h->d_mass_pool ? h->d_mass_pool + (size_t)h->cur_buf * (h->cfg.mass_capacity + 64) : nullptr;
   h->segs.clear();
   h->pos_used = 0;
   h->mass_used = 0;
@@ -630,6 +671,25 @@ static void fill_segment(const slicer_handle *h, const Segment &s, SegmentDev *D
   D->layout = s.layout;
 }
 
+// fold the device time of the oldest `n` pending passes (all if n == 0) into the stats; blocks until they finished
+static int resolve_passes(slicer_handle *h, size_t n)
+{
+  size_t upto = n ? h->pass_tail + n : h->pass_head;
+  if (upto > h->pass_head)
+    upto = h->pass_head;
+  for (; h->pass_tail < upto; h->pass_tail++)
+  {
+    cudaEvent_t e0 = h->pass_ev[2 * (h->pass_tail % PASS_RING)], e1 = h->pass_ev[2 * (h->pass_tail % PASS_RING) + 1];
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    h->stats.last_deposit_ms = ms;
+    h->stats.deposit_ms_sum += ms;
+    h->stats.deposit_passes++;
+  }
+  return 0;
+}
+
 static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplanes, bool accumulate)
 {
   if (!h || !planes)
@@ -653,7 +713,10 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
   int kernel = h->cfg.kernel;
   if (kernel == SLICER_KERNEL_AUTO)
     kernel = SLICER_KERNEL_PIPELINED;
-  CU(cudaEventRecord(h->ev_start, h->compute));
+  if (h->pass_head - h->pass_tail == PASS_RING && resolve_passes(h, 1))
+    return 1;
+  cudaEvent_t e0 = h->pass_ev[2 * (h->pass_head % PASS_RING)], e1 = h->pass_ev[2 * (h->pass_head % PASS_RING) + 1];
+  CU(cudaEventRecord(e0, h->compute));
   for (size_t si = 0; si < h->segs.size(); si++)
   {
     SegmentDev D;
@@ -677,11 +740,12 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
       CU(cudaGetLastError());
     }
     h->stats.launches++;
+    h->stats.deposit_launches++;
     h->stats.particles_streamed += D.n;
   }
-  CU(cudaEventRecord(h->ev_stop, h->compute));
-  CU(cudaEventRecord(h->ev_pass_done, h->compute));
-  h->have_timing = true;
+  CU(cudaEventRecord(e1, h->compute));
+  CU(cudaEventRecord(h->ev_buf_done[h->cur_buf], h->compute));
+  h->pass_head++;
   return 0;
 }
 
@@ -779,13 +843,8 @@ extern "C" int slicer_get_stats(slicer_handle *h, slicer_stats *out)
     return fail("null argument");
   if (set_device(h))
     return 1;
-  if (h->have_timing)
-  {
-    CU(cudaEventSynchronize(h->ev_stop));
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop));
-    h->stats.last_deposit_ms = ms;
-  }
+  if (resolve_passes(h, 0))
+    return 1;
   size_t res = 0;
   for (size_t i = 0; i < h->segs.size(); i++)
     res += h->segs[i].n;
@@ -793,6 +852,45 @@ extern "C" int slicer_get_stats(slicer_handle *h, slicer_stats *out)
   h->stats.device_bytes = h->device_bytes;
   h->stats.sm_count = h->sm_count;
   *out = h->stats;
+  return 0;
+}
+
+extern "C" int slicer_reset_stats(slicer_handle *h)
+{
+  if (!h)
+    return fail("null handle");
+  if (set_device(h) || resolve_passes(h, 0))
+    return 1;
+  h->stats.deposit_ms_sum = 0;
+  h->stats.deposit_passes = 0;
+  h->stats.deposit_launches = 0;
+  h->stats.launches = 0;
+  h->stats.particles_streamed = 0;
+  return 0;
+}
+
+extern "C" int slicer_timer_begin(slicer_handle *h)
+{
+  if (!h)
+    return fail("null handle");
+  if (set_device(h))
+    return 1;
+  CU(cudaEventRecord(h->ev_t0, h->compute));
+  return 0;
+}
+
+extern "C" int slicer_timer_end(slicer_handle *h, double *ms)
+{
+  if (!h || !ms)
+    return fail("null argument");
+  if (set_device(h))
+    return 1;
+  CU(cudaStreamSynchronize(h->copy));
+  CU(cudaEventRecord(h->ev_t1, h->compute));
+  CU(cudaEventSynchronize(h->ev_t1));
+  float f = 0;
+  CU(cudaEventElapsedTime(&f, h->ev_t0, h->ev_t1));
+  *ms = f;
   return 0;
 }
 

@@ -46,7 +46,7 @@ def run_plane(types, plane, npix, mas, kernel, layout=capi.LAYOUT_AOS, massarr=N
         return out
 
 
-def check_against_oracle(oracle, types, plane, npix, got, do_ngp, mass_scale):
+def check_against_oracle(oracle, types, plane, npix, got, do_ngp, mass_scale, strict_float=True):
     res = oracle.plane_from_particles(types, plane, npix, do_ngp=do_ngp, frac_bits=got["frac_bits"])
     assert got["counts"].tolist() == res["counts"].tolist()
     assert got["ingrid"].tolist() == res["ingrid"].tolist()
@@ -54,8 +54,12 @@ def check_against_oracle(oracle, types, plane, npix, got, do_ngp, mass_scale):
         ty = t["type"]
         # int64 fixed point: bit exact
         assert np.array_equal(got["fixed"][ty], res["fixed"][ty]), f"type {ty}: fixed-point accumulators differ"
-        # float map vs the reference's float32-in-order map: 1e-6 relative + floor
-        np.testing.assert_allclose(got["maps"][ty], res["maps"][ty], rtol=1e-6, atol=1e-9 * mass_scale)
+        # float map vs the exact sum of the reference's contributions, and vs the reference's float32-in-order map:
+        # 1e-6 relative + floor.  (With thousands of particles per pixel the reference's own float32 running sum is
+        # off by more than 1e-6 from the exact sum - BASELINE.md §2 - so that comparison is skipped there.)
+        np.testing.assert_allclose(got["maps"][ty], res["f64"][ty], rtol=1e-6, atol=1e-9 * mass_scale)
+        if strict_float:
+            np.testing.assert_allclose(got["maps"][ty], res["maps"][ty], rtol=1e-6, atol=1e-9 * mass_scale)
         # mass conservation against the exact sum of the same contributions
         tot = res["f64"][ty].sum()
         if tot > 0:
@@ -137,7 +141,7 @@ def test_clustered_particles_contention(oracle):
     plane = dict(boxsize=box, sgn=[1, 1, 1], face=1, centre=[0.0, 0.0, 0.0], rcase=0.0, ld=0.0, ld2=64.0, nrepperp=0,
                  fovradiants=1.2)
     got = run_plane(types, plane, 64, capi.MAS_TSC, capi.KERNEL_PIPELINED, massarr=[0, 0.5, 0, 0, 0, 0])
-    check_against_oracle(oracle, types, plane, 64, got, False, 0.5)
+    check_against_oracle(oracle, types, plane, 64, got, False, 0.5, strict_float=False)
 
 
 def test_accumulate_over_subfiles(oracle):
