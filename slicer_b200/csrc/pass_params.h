@@ -30,7 +30,7 @@ struct XformDev
   float thr_m;      // additive slack of the lateral test: screen error + tmax * (z error)
   float zlo_m, zhi_m; // zmin/zmax widened by the screen's error margin
   float zamb;       // z-wrap ambiguity: |w - 0.5| > zamb  => undecidable
-  float raw_half, raw_amb; // |raw - raw_half| > raw_amb => raw within margin of a box face (or outside)
+  float raw_hi;     // raw coordinates outside the open interval (0, raw_hi) may wrap in the exact chain => undecidable
 };
 
 struct PlaneDev

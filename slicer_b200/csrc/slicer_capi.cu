@@ -653,8 +653,7 @@ static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int npl
     X.zhi_m = X.zmax + mz;
     X.zamb = 0.5f - 2e-6f;
     X.thr_m = isinf(X.tmax) ? 0.f : 4e-6f + X.tmax * mz * 1.01f;
-    X.raw_half = (float)(0.5 * h->boxsize);
-    X.raw_amb = (float)(h->boxsize * (0.5 - 4e-6));
+    X.raw_hi = float_floor(h->boxsize * (1.0 - 1e-6)); // 0 < raw < raw_hi  =>  raw/box in (0,1): no wrap at the first site
   }
   return 0;
 }
