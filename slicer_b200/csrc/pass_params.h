@@ -50,6 +50,10 @@ struct PlaneDev
   double half_dl;    // 0.5*dx                          utilities.cpp:9
   double onehalf_dl; // 0.5*3.0*dx                      utilities.cpp:11
   double scale;      // 2^frac_bits
+  float scalef;      // the same as a float (exact)
+  float dlf, half_dlf, onehalf_dlf; // float copies of dl, 0.5*dl, 1.5*dl: exact when npix is a power of two
+  double arg_lim;    // small-angle series: valid (and sufficient) for |X/d|, |Y/Z| <= arg_lim
+  int nt;            // terms of the small-angle series, 0 => use libdevice asin/atan2 (wide fields)
   unsigned long long *acc;    // this plane's accumulators: [ntypes_alloc][npix*npix] int64 fixed point
   unsigned long long *counts; // [SLICER_NTYPES][2]: accepted pairs, in-grid pairs
   unsigned long long type_stride; // npix*npix when per-type maps are kept, else 0
@@ -59,6 +63,8 @@ struct PassParams
 {
   int nxform;
   int nplanes;
+  int fast;  // every plane: npix a power of two, no perpendicular replication, disjoint slabs per randomisation
+  int debug; // measurement aid (env SLICER_B200_DEBUG): bit0 skip the map atomics, bit1 skip the exact chain; 0 in production
   XformDev xf[SLICER_MAX_XFORMS];
   PlaneDev pl[SLICER_MAX_PLANES];
 };

@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -123,6 +124,8 @@ struct slicer_handle
   std::vector<cudaEvent_t> pass_ev;                // ring of (start, stop) pairs, resolved lazily
   size_t pass_head = 0, pass_tail = 0;             // pairs [tail, head) are pending
   int nbuf = 1, cur_buf = 0;
+  int debug = 0;
+  bool no_series = false; // env SLICER_B200_NO_SERIES: always use libdevice asin/atan2 (A/B checks)
   float *d_pos_pool = nullptr;  // nbuf * (particle_capacity * 3 + 64) floats
   float *d_mass_pool = nullptr; // nbuf * (mass_capacity + 64) floats
   float *d_pos = nullptr;  // current pool
@@ -207,6 +210,9 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
   if (h->cfg.max_m <= 0)
     h->cfg.max_m = 1e3; /* densitymaps.h:21 */
   h->ntypes_alloc = cfg->per_type_maps ? SLICER_NTYPES : 1;
+  h->no_series = getenv("SLICER_B200_NO_SERIES") != nullptr;
+  if (const char *dbg = getenv("SLICER_B200_DEBUG"))
+    h->debug = atoi(dbg);
   h->npix2max = (size_t)cfg->npix_max * (size_t)cfg->npix_max;
   memset(&h->stats, 0, sizeof(h->stats));
   memset(h->plane_npix, 0, sizeof(h->plane_npix));
@@ -572,6 +578,8 @@ static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int npl
   }
   P->nxform = nx;
   P->nplanes = nplanes;
+  P->debug = h->debug;
+  P->fast = 1;
   static const int perm_of_face[7][3] = {{0, 1, 2}, {0, 1, 2}, {0, 2, 1}, {1, 2, 0}, {1, 0, 2}, {2, 0, 1}, {2, 1, 0}}; /* gadget2io.cpp:223-252 */
   int slot = 0;
   for (int t = 0; t < nx; t++)
@@ -620,6 +628,10 @@ static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int npl
       L.half_dl = 0.5 * L.dl;      /* utilities.cpp:9  */
       L.onehalf_dl = 0.5 * 3.0 * L.dl; /* utilities.cpp:11 */
       L.scale = ldexp(1.0, h->frac_bits);
+      L.scalef = (float)L.scale;
+      L.dlf = (float)L.dl;
+      L.half_dlf = (float)L.half_dl;
+      L.onehalf_dlf = (float)L.onehalf_dl;
       if (L.T < 1.5)
       {
         const double tt = tan(L.T) * (1.0 + 1e-5);
@@ -631,10 +643,30 @@ static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int npl
         L.pre_tx = INFINITY;
         L.pre_ty = INFINITY;
       }
+      // small-angle series for asin/atan (device_chain.cuh): enough terms that arg_lim^(2 nt) < 2^-55
+      L.nt = 0;
+      L.arg_lim = 0;
+      if (!h->no_series && isfinite(L.pre_tx) && (double)L.pre_tx * 1.01 <= 0.385)
+      {
+        L.arg_lim = (double)L.pre_tx * 1.01;
+        L.nt = (int)ceil(55.0 * log(2.0) / (2.0 * log(1.0 / L.arg_lim)));
+        if (L.nt < 2)
+          L.nt = 2;
+        if (L.nt > 20)
+          L.nt = 0;
+      }
       L.acc = h->d_acc + (size_t)i * h->ntypes_alloc * h->npix2max;
       L.counts = h->d_counts + (size_t)i * SLICER_NTYPES * 2;
       L.type_stride = h->cfg.per_type_maps ? h->npix2max : 0;
       h->plane_npix[i] = d.npix;
+    }
+    for (int a = X.first_plane; a < X.first_plane + X.nplanes; a++)
+    {
+      if (!P->pl[a].pow2 || P->pl[a].nrep != 0)
+        P->fast = 0;
+      for (int b = a + 1; b < X.first_plane + X.nplanes; b++)
+        if (P->pl[a].zlo < P->pl[b].zhi && P->pl[b].zlo < P->pl[a].zhi)
+          P->fast = 0; // overlapping slabs: a particle can belong to two planes
     }
     // float screen of the pipelined kernel (deposit_pipelined.cuh: screen()); all margins are >= 5x the
     // worst-case difference between the screen's coordinates and the exact chain's
