@@ -21,6 +21,7 @@ NTYPES = 6
 MAS_TSC, MAS_NGP = 0, 1
 LAYOUT_AOS, LAYOUT_SOA = 0, 1
 KERNEL_AUTO, KERNEL_SIMPLE, KERNEL_PIPELINED = 0, 1, 2
+DEPOSIT_AUTO, DEPOSIT_DIRECT, DEPOSIT_BINNED = 0, 1, 2
 
 
 class SlicerError(RuntimeError):
@@ -40,6 +41,8 @@ class Config(C.Structure):
         ("mass_capacity", C.c_size_t),
         ("kernel", C.c_int),
         ("staging_buffers", C.c_int),
+        ("deposit_mode", C.c_int),
+        ("record_capacity", C.c_size_t),
     ]
 
 
@@ -191,10 +194,12 @@ class Slicer:
 
     def __init__(self, npix_max: int, max_planes: int = 4, mas: int = MAS_TSC, particle_capacity: int = 0,
                  mass_capacity: int = 0, per_type_maps: bool = False, device: int = 0, kernel: int = KERNEL_AUTO,
-                 frac_bits: int = 0, max_m: float = 1e3, staging_buffers: int = 1):
+                 frac_bits: int = 0, max_m: float = 1e3, staging_buffers: int = 1, deposit_mode: int = DEPOSIT_AUTO,
+                 record_capacity: int = 0):
         cfg = Config(device=device, mas=mas, max_m=max_m, frac_bits=frac_bits, max_planes=max_planes,
                      npix_max=npix_max, per_type_maps=int(per_type_maps), particle_capacity=particle_capacity,
-                     mass_capacity=mass_capacity, kernel=kernel, staging_buffers=staging_buffers)
+                     mass_capacity=mass_capacity, kernel=kernel, staging_buffers=staging_buffers, deposit_mode=deposit_mode,
+                     record_capacity=record_capacity)
         h = C.c_void_p()
         _check(lib().slicer_create(C.byref(cfg), C.byref(h)))
         self.h = h

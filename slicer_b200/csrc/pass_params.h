@@ -64,6 +64,8 @@ struct PassParams
   int nxform;
   int nplanes;
   int fast;  // every plane: npix a power of two, no perpendicular replication, disjoint slabs per randomisation
+  int pair;  // fast, and all planes share one field (T, fovrad) with a small-angle series: two survivors per lane
+  double est_accept; // host estimate of the accepted fraction of a uniform snapshot (chooses the deposit path)
   int debug; // measurement aid (env SLICER_B200_DEBUG): bit0 skip the map atomics, bit1 skip the exact chain; 0 in production
   XformDev xf[SLICER_MAX_XFORMS];
   PlaneDev pl[SLICER_MAX_PLANES];

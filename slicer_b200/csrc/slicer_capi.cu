@@ -147,6 +147,16 @@ struct slicer_handle
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
   PipelinedScratch pipe;
+  // binned deposit (deposit_binned.cuh): buffers allocated on first use
+  struct
+  {
+    float2 *rec_u = nullptr, *rec_s = nullptr;
+    unsigned short *key_u = nullptr;
+    float *mass_u = nullptr, *mass_s = nullptr;
+    unsigned *region_count = nullptr, *region_hist = nullptr, *bin_count = nullptr, *bin_start = nullptr;
+    size_t slice = 0;    // particles per slice
+    size_t capacity = 0; // records the buffers hold
+  } bin;
 };
 
 static int set_device(slicer_handle *h)
@@ -309,6 +319,15 @@ extern "C" void slicer_destroy(slicer_handle *h)
   if (h->comm && g_nccl.CommDestroy)
     g_nccl.CommDestroy(h->comm);
   pipelined_destroy(&h->pipe);
+  cudaFree(h->bin.rec_u);
+  cudaFree(h->bin.rec_s);
+  cudaFree(h->bin.key_u);
+  cudaFree(h->bin.mass_u);
+  cudaFree(h->bin.mass_s);
+  cudaFree(h->bin.region_count);
+  cudaFree(h->bin.bin_count);
+  cudaFree(h->bin.bin_start);
+  cudaFree(h->bin.region_hist);
   cudaFree(h->d_pos_pool);
   cudaFree(h->d_mass_pool);
   cudaFree(h->d_acc);
@@ -580,6 +599,8 @@ static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int npl
   P->nplanes = nplanes;
   P->debug = h->debug;
   P->fast = 1;
+  P->est_accept = 0;
+  P->pair = 0;
   static const int perm_of_face[7][3] = {{0, 1, 2}, {0, 1, 2}, {0, 2, 1}, {1, 2, 0}, {1, 0, 2}, {2, 0, 1}, {2, 1, 0}}; /* gadget2io.cpp:223-252 */
   int slot = 0;
   for (int t = 0; t < nx; t++)
@@ -659,6 +680,11 @@ static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int npl
       L.counts = h->d_counts + (size_t)i * SLICER_NTYPES * 2;
       L.type_stride = h->cfg.per_type_maps ? h->npix2max : 0;
       h->plane_npix[i] = d.npix;
+      {
+        // fraction of a uniform snapshot this plane accepts: slab thickness x (field width / box)^2 at mid-distance
+        const double w = L.T < 1.5 ? 2.0 * tan(L.T) * 0.5 * (minDist + maxDist) : 1.0;
+        P->est_accept += (maxDist - minDist) * (w < 1.0 ? w * w : 1.0);
+      }
     }
     for (int a = X.first_plane; a < X.first_plane + X.nplanes; a++)
     {
@@ -687,6 +713,10 @@ static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int npl
     X.thr_m = isinf(X.tmax) ? 0.f : 4e-6f + X.tmax * mz * 1.01f;
     X.raw_hi = float_floor(h->boxsize * (1.0 - 1e-6)); // 0 < raw < raw_hi  =>  raw/box in (0,1): no wrap at the first site
   }
+  P->pair = P->fast && P->pl[0].nt > 0;
+  for (int q = 1; q < P->nplanes; q++)
+    if (P->pl[q].T != P->pl[0].T || P->pl[q].fovrad != P->pl[0].fovrad || P->pl[q].npix != P->pl[0].npix)
+      P->pair = 0;
   return 0;
 }
 
@@ -700,6 +730,102 @@ static void fill_segment(const slicer_handle *h, const Segment &s, SegmentDev *D
   D->max_m = float_floor(h->cfg.max_m);      /* float m > double MAX_M  <=>  m > largest float <= MAX_M */
   D->type = s.type;
   D->layout = s.layout;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// binned deposit: K1 (records) -> histogram -> scan -> scatter -> tile deposit, slice by slice
+// ------------------------------------------------------------------------------------------------------------
+static int binned_tiles(const PassParams &P) { return (P.pl[0].npix + binned::TILE - 1) / binned::TILE; }
+
+static bool use_binned(const slicer_handle *h, const PassParams &P, const SegmentDev &D)
+{
+  if (h->cfg.mas != SLICER_MAS_TSC || !P.fast || h->cfg.deposit_mode == SLICER_DEPOSIT_DIRECT)
+    return false;
+  for (int q = 1; q < P.nplanes; q++)
+    if (P.pl[q].npix != P.pl[0].npix)
+      return false;
+  const int nt = binned_tiles(P);
+  if ((long long)P.nplanes * nt * nt > binned::MAX_BINS)
+    return false;
+  if (h->cfg.deposit_mode == SLICER_DEPOSIT_BINNED)
+    return true;
+  if (D.n < (1ull << 22))
+    return false;
+  return P.est_accept > 0.01;
+}
+
+static int binned_alloc(slicer_handle *h)
+{
+  if (h->bin.rec_u)
+    return 0;
+  size_t slice = h->cfg.record_capacity ? h->cfg.record_capacity : ((size_t)1 << 28);
+  size_t cap_particles = h->cfg.particle_capacity ? h->cfg.particle_capacity : slice;
+  if (slice > cap_particles)
+    slice = cap_particles;
+  slice = (slice + pipe::CHUNK - 1) / pipe::CHUNK * pipe::CHUNK;
+  const size_t cap = slice + (size_t)h->pipe.grid_max * pipe::CHUNK; // every warp region is rounded up to whole chunks
+  if (dev_alloc(h, &h->bin.rec_u, cap) || dev_alloc(h, &h->bin.rec_s, cap) || dev_alloc(h, &h->bin.key_u, cap))
+    return 1;
+  if (h->cfg.mass_capacity && (dev_alloc(h, &h->bin.mass_u, cap) || dev_alloc(h, &h->bin.mass_s, cap)))
+    return 1;
+  if (dev_alloc(h, &h->bin.region_count, (size_t)h->pipe.grid_max * pipe::NCONS) ||
+      dev_alloc(h, &h->bin.region_hist, (size_t)binned::MAX_BINS * h->pipe.grid_max * pipe::NCONS) ||
+      dev_alloc(h, &h->bin.bin_count, (size_t)binned::MAX_BINS) || dev_alloc(h, &h->bin.bin_start, (size_t)binned::MAX_BINS + 1))
+    return 1;
+  h->bin.slice = slice;
+  h->bin.capacity = cap;
+  return 0;
+}
+
+static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &D)
+{
+  if (binned_alloc(h))
+    return 1;
+  const int nt = binned_tiles(P);
+  const int nbins = P.nplanes * nt * nt;
+  for (unsigned long long off = 0; off < D.n; off += h->bin.slice)
+  {
+    SegmentDev S = D;
+    S.n = D.n - off < h->bin.slice ? D.n - off : h->bin.slice;
+    S.pos = D.layout == SLICER_LAYOUT_AOS ? D.pos + 3ull * off : D.pos + off;
+    S.mass = D.mass ? D.mass + off : nullptr;
+    const int grid = pipelined_grid(&h->pipe, S.n);
+    const unsigned long long nchunks = (S.n + pipe::CHUNK - 1) / pipe::CHUNK;
+    const unsigned long long cmax = (nchunks + grid - 1) / grid;
+    binned::EmitDev E;
+    E.rec = h->bin.rec_u;
+    E.key = h->bin.key_u;
+    E.mass = D.mass ? h->bin.mass_u : nullptr;
+    E.region_count = h->bin.region_count;
+    E.region_cap = cmax * (pipe::CHUNK / pipe::NCONS);
+    E.ntile = nt;
+    const int nregions = grid * pipe::NCONS;
+    if ((unsigned long long)nregions * E.region_cap > h->bin.capacity)
+      return fail("binned deposit: record buffer too small (internal error)");
+    binned::SortDev Q;
+    Q.rec_u = h->bin.rec_u;
+    Q.key_u = h->bin.key_u;
+    Q.mass_u = E.mass;
+    Q.region_count = h->bin.region_count;
+    Q.region_cap = E.region_cap;
+    Q.nregions = nregions;
+    Q.nbins = nbins;
+    Q.region_hist = h->bin.region_hist;
+    Q.bin_count = h->bin.bin_count;
+    Q.bin_start = h->bin.bin_start;
+    Q.rec_s = h->bin.rec_s;
+    Q.mass_s = D.mass ? h->bin.mass_s : nullptr;
+    if (pipelined_launch_emit(grid, P, S, E, h->compute))
+      return fail("record kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    binned::bin_histogram_kernel<<<nregions, binned::SCATTER_THREADS, 0, h->compute>>>(Q);
+    binned::bin_region_scan_kernel<<<nbins, 1024, 0, h->compute>>>(Q);
+    binned::bin_scan_kernel<<<1, 1024, 0, h->compute>>>(Q);
+    binned::bin_scatter_kernel<<<nregions, binned::SCATTER_THREADS, 0, h->compute>>>(Q);
+    binned::tile_deposit_kernel<<<nbins, binned::DEPOSIT_THREADS, binned::TCELLS * 8, h->compute>>>(P, Q, nt, D.type, D.const_mass);
+    CU(cudaGetLastError());
+    h->stats.launches += 5;
+  }
+  return 0;
 }
 
 // fold the device time of the oldest `n` pending passes (all if n == 0) into the stats; blocks until they finished
@@ -756,7 +882,12 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
       continue;
     if (kernel == SLICER_KERNEL_PIPELINED)
     {
-      if (pipelined_launch(&h->pipe, h->cfg.mas, P, D, h->compute))
+      if (use_binned(h, P, D))
+      {
+        if (binned_pass(h, P, D))
+          return 1;
+      }
+      else if (pipelined_launch(&h->pipe, h->cfg.mas, P, D, h->compute))
         return fail("pipelined launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     else

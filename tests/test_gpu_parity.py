@@ -23,10 +23,11 @@ def stage_types(s, types, layout=capi.LAYOUT_AOS):
         s.stage(t["type"], pos, t.get("masses"), layout=layout)
 
 
-def run_plane(types, plane, npix, mas, kernel, layout=capi.LAYOUT_AOS, massarr=None, hydro=False, per_type=True):
+def run_plane(types, plane, npix, mas, kernel, layout=capi.LAYOUT_AOS, massarr=None, hydro=False, per_type=True,
+              deposit_mode=capi.DEPOSIT_AUTO, record_capacity=0):
     n = sum(len(t["raw"]) for t in types) + 64
     with capi.Slicer(npix_max=npix, max_planes=1, mas=mas, particle_capacity=n, mass_capacity=n, per_type_maps=per_type,
-                     kernel=kernel) as s:
+                     kernel=kernel, deposit_mode=deposit_mode, record_capacity=record_capacity) as s:
         s.begin_snapshot(plane["boxsize"], massarr, hydro)
         stage_types(s, types, layout)
         d = capi.plane_desc(plane["sgn"], plane["face"], plane["centre"], plane["rcase"], plane["ld"], plane["ld2"],
@@ -197,3 +198,61 @@ def test_errors_are_loud():
             s.fetch(0, 3, 32)  # per-type maps not requested
     with pytest.raises(capi.SlicerError):
         capi.Slicer(npix_max=32, max_planes=99)
+
+
+@pytest.mark.parametrize("name", ["dm_face1", "hydro_multi"])
+def test_binned_deposit_golden(oracle, golden, name):
+    """The shared-memory tile path (records -> counting sort -> tiles) gives the same int64 maps (power-of-two maps)."""
+    m = golden.meta[name]
+    types, plane = golden.types(name), golden.plane(name)
+    got = run_plane(types, plane, m["npix"], capi.MAS_TSC, capi.KERNEL_PIPELINED, massarr=m["massarr"], hydro=bool(m["hydro"]),
+                    deposit_mode=capi.DEPOSIT_BINNED)
+    assert got["counts"].tolist() == m["counts"]
+    check_against_oracle(oracle, types, plane, m["npix"], got, False, 1.0)
+
+
+@pytest.mark.parametrize("layout", [capi.LAYOUT_AOS, capi.LAYOUT_SOA])
+@pytest.mark.parametrize("npix,fov,cap", [(256, 0.9, 0), (512, 0.35, 40960), (128, 0.8, 8192)])
+def test_binned_deposit_slices_and_borders(oracle, npix, fov, cap, layout):
+    """Several tiles per map, several slices per pass, stencils on the map border, ragged particle count."""
+    box = 128000.0
+    n = 150001
+    pos = synth.uniform_positions(n, box, 31)
+    types = [dict(type=1, raw=pos, const_mass=0.8125)]
+    plane = dict(boxsize=box, sgn=[-1, 1, 1], face=4, centre=[0.125, 0.625, 0.375], rcase=1.0, ld=128.0, ld2=128.0 + 96.0,
+                 nrepperp=0, fovradiants=fov)
+    got = run_plane(types, plane, npix, capi.MAS_TSC, capi.KERNEL_PIPELINED, layout=layout, massarr=[0, 0.8125, 0, 0, 0, 0],
+                    deposit_mode=capi.DEPOSIT_BINNED, record_capacity=cap)
+    res = check_against_oracle(oracle, types, plane, npix, got, False, 0.8125)
+    assert res["counts"][1] > 1000 and res["ingrid"][1] < res["counts"][1]  # some nearest grid points fall outside the map
+
+
+def test_binned_multi_plane_multi_xform(oracle):
+    """Binned pass over 8 planes of 2 randomisations == direct pass == oracle."""
+    box = 128000.0
+    n = 300000
+    pos = synth.uniform_positions(n, box, 6)
+    types = [dict(type=1, raw=pos, const_mass=1.0375)]
+    rnd = oracle.randomize_box(-229, -230, -231, [1, 0, 0, 0, 1, 0, 0, 0])
+    fov = float(np.float32(20.0)) / 180.0 * np.pi
+    npix = 256
+    planes = []
+    for i in range(8):
+        planes.append(dict(boxsize=box, sgn=[rnd["sgnX"][i], rnd["sgnY"][i], rnd["sgnZ"][i]], face=rnd["face"][i],
+                           centre=[rnd["x0"][i], rnd["y0"][i], rnd["z0"][i]], rcase=float(i // 4), ld=32.0 * i, ld2=32.0 * (i + 1),
+                           nrepperp=0, fovradiants=fov))
+    descs = [capi.plane_desc(p["sgn"], p["face"], p["centre"], p["rcase"], p["ld"], p["ld2"], fov, npix) for p in planes]
+    fixed = {}
+    for mode in (capi.DEPOSIT_DIRECT, capi.DEPOSIT_BINNED):
+        with capi.Slicer(npix_max=npix, max_planes=8, mas=capi.MAS_TSC, particle_capacity=n + 64, deposit_mode=mode,
+                         record_capacity=100000) as s:
+            s.begin_snapshot(box, [0, 1.0375, 0, 0, 0, 0], False)
+            s.stage(1, pos)
+            s.deposit(descs)
+            fb = s.frac_bits
+            fixed[mode] = [s.fetch_fixed(k, -1, npix).reshape(-1) for k in range(8)]
+            counts = [s.fetch(k, -1, npix, want_map=False)[1] for k in range(8)]
+        for k, p in enumerate(planes):
+            res = oracle.plane_from_particles(types, p, npix, frac_bits=fb)
+            assert counts[k].tolist() == res["counts"].tolist()
+            assert np.array_equal(fixed[mode][k], res["fixed"][1]), (mode, k)
