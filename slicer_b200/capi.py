@@ -82,7 +82,7 @@ EXPORTS = [
     "slicer_stage_synthetic", "slicer_download_segment", "slicer_deposit", "slicer_deposit_accumulate",
     "slicer_reduce", "slicer_fetch", "slicer_fetch_fixed", "slicer_synchronize", "slicer_get_stats",
     "slicer_frac_bits", "slicer_comm_unique_id", "slicer_comm_init_rank", "slicer_comm_init_all",
-    "slicer_reduce_all", "slicer_reset_stats", "slicer_timer_begin", "slicer_timer_end",
+    "slicer_reduce_all", "slicer_wait_staging", "slicer_reset_stats", "slicer_timer_begin", "slicer_timer_end",
 ]
 
 
@@ -128,6 +128,7 @@ def lib() -> C.CDLL:
     L.slicer_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.slicer_fetch_fixed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.slicer_synchronize.argtypes = [C.c_void_p]
+    L.slicer_wait_staging.argtypes = [C.c_void_p]
     L.slicer_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
     L.slicer_frac_bits.argtypes = [C.c_void_p]
     L.slicer_comm_unique_id.argtypes = [C.c_char_p]
@@ -288,6 +289,9 @@ class Slicer:
 
     def synchronize(self):
         _check(lib().slicer_synchronize(self.h))
+
+    def wait_staging(self):
+        _check(lib().slicer_wait_staging(self.h))
 
     def fetch(self, plane: int, ptype: int = -1, npix: Optional[int] = None, want_map: bool = True):
         """-> (map float32 [npix, npix] indexed [gy, gx] or None, counts int64[6], ingrid int64[6])"""

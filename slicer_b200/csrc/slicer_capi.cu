@@ -932,6 +932,16 @@ extern "C" int slicer_synchronize(slicer_handle *h)
   return 0;
 }
 
+extern "C" int slicer_wait_staging(slicer_handle *h)
+{
+  if (!h)
+    return fail("null handle");
+  if (set_device(h))
+    return 1;
+  CU(cudaStreamSynchronize(h->copy));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // read-out
 // ------------------------------------------------------------------------------------------------------------

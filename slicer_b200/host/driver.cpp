@@ -1,0 +1,385 @@
+// driver.cpp — createDensityMaps on the GPU and the plane driver of main() (slicer-v2.cpp:130-230), restructured:
+// the reference walks the PLANES and re-reads + re-transforms a whole snapshot for each one (:138-207); here the
+// loop is over SNAPSHOTS, every sub-file is read once into page-locked memory, copied once, and one CUDA pass
+// deposits it into all the planes that use the snapshot.  Sub-files are dealt round-robin to the GPUs of the box
+// (the reference deals them to MPI ranks, :162-175) and the planes are summed with ncclReduce instead of MPI_Reduce.
+#include "slicer_host.h"
+
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+namespace slicer
+{
+
+struct Engine
+{
+  std::vector<int> devices;
+  std::vector<slicer_handle *> h;
+  std::vector<SubFile> bufs; // two page-locked sub-file buffers per GPU
+  std::vector<int> used;     // sub-files staged on each GPU since begin
+  int npix_max = 0, mas = SLICER_MAS_TSC, deposit_mode = SLICER_DEPOSIT_AUTO;
+  bool per_type = false;
+  size_t capacity = 0;
+  bool comm = false;
+};
+
+static int make_handles(Engine *e)
+{
+  for (auto *hh : e->h)
+    slicer_destroy(hh);
+  e->h.assign(e->devices.size(), nullptr);
+  e->comm = false;
+  for (size_t g = 0; g < e->devices.size(); g++)
+  {
+    slicer_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.device = e->devices[g];
+    cfg.mas = e->mas;
+    cfg.max_m = MAX_M;
+    cfg.max_planes = SLICER_MAX_PLANES;
+    cfg.npix_max = e->npix_max;
+    cfg.per_type_maps = e->per_type;
+    cfg.particle_capacity = e->capacity;
+    cfg.mass_capacity = e->capacity;
+    cfg.kernel = SLICER_KERNEL_AUTO;
+    cfg.staging_buffers = 2;
+    cfg.deposit_mode = e->deposit_mode;
+    if (slicer_create(&cfg, &e->h[g]))
+    {
+      std::cerr << "slicer_create failed: " << slicer_last_error() << std::endl;
+      return 1;
+    }
+  }
+  if (e->h.size() > 1)
+  {
+    if (slicer_comm_init_all(e->h.data(), (int)e->h.size()))
+    {
+      std::cerr << "NCCL communicator: " << slicer_last_error() << std::endl;
+      return 1;
+    }
+    e->comm = true;
+  }
+  return 0;
+}
+
+Engine *engineCreate(const std::vector<int> &devices, int npix_max, int mas, bool per_type_maps, size_t particle_capacity, int deposit_mode)
+{
+  Engine *e = new Engine;
+  e->devices = devices;
+  e->npix_max = npix_max;
+  e->mas = mas;
+  e->per_type = per_type_maps;
+  e->capacity = particle_capacity;
+  e->deposit_mode = deposit_mode;
+  e->bufs = std::vector<SubFile>(2 * devices.size());
+  e->used.assign(devices.size(), 0);
+  if (make_handles(e))
+  {
+    engineDestroy(e);
+    return nullptr;
+  }
+  return e;
+}
+
+void engineDestroy(Engine *e)
+{
+  if (!e)
+    return;
+  for (auto *hh : e->h)
+    slicer_destroy(hh);
+  delete e;
+}
+
+int engineGpuCount(const Engine *e) { return (int)e->h.size(); }
+
+static slicer_plane_desc make_desc(const Lens &lens, const Random &random, int isnap, double rcase, double fovradiants, int npix)
+{
+  slicer_plane_desc d;
+  memset(&d, 0, sizeof(d));
+  d.sgn[0] = random.sgnX[isnap];
+  d.sgn[1] = random.sgnY[isnap];
+  d.sgn[2] = random.sgnZ[isnap];
+  d.face = random.face[isnap];
+  d.centre[0] = random.x0[isnap];
+  d.centre[1] = random.y0[isnap];
+  d.centre[2] = random.z0[isnap];
+  d.rcase = (float)rcase; // createDensityMaps takes a double, readPos a float (densitymaps.h:162, gadget2io.h:123)
+  d.ld = lens.ld[isnap];
+  d.ld2 = lens.ld2[isnap];
+  d.nrepperp = lens.nrepperp.empty() ? 0 : lens.nrepperp[isnap];
+  d.fovradiants = fovradiants;
+  d.npix = npix;
+  return d;
+}
+
+static int fail_capi(const char *what)
+{
+  std::cerr << what << ": " << slicer_last_error() << std::endl;
+  return 1;
+}
+
+int createDensityMapsMulti(Engine *e, InputParams &p, Lens &lens, Random &random, const std::vector<PlaneJob> &jobs, unsigned ffmin,
+                           unsigned ffmax, const std::string &File, double fovradiants, std::vector<std::valarray<float>> &mapxytot,
+                           std::vector<std::valarray<float>> &mapxytoti, std::vector<long long> &ntotxyi, int myid)
+{
+  if (p.snopt > 0)
+  {
+    std::cerr << "Part. Degradation (snopt > 0) is not implemented on the GPU path yet" << std::endl;
+    return 1;
+  }
+  const int njobs = (int)jobs.size();
+  mapxytot.assign(njobs, std::valarray<float>());
+  mapxytoti.assign((size_t)njobs * 6, std::valarray<float>());
+  ntotxyi.assign((size_t)njobs * 6, 0);
+  const int ngpu = (int)e->h.size();
+  for (int j0 = 0; j0 < njobs; j0 += SLICER_MAX_PLANES)
+  {
+    const int nj = std::min(njobs - j0, (int)SLICER_MAX_PLANES);
+    std::vector<slicer_plane_desc> descs;
+    for (int j = 0; j < nj; j++)
+      descs.push_back(make_desc(lens, random, jobs[j0 + j].isnap, jobs[j0 + j].rcase, fovradiants, jobs[j0 + j].npix));
+    std::fill(e->used.begin(), e->used.end(), 0);
+    Header first_header;
+    bool have_header = false;
+    for (unsigned ff = ffmin; ff < ffmax; ff++)
+    {
+      const int g = (int)((ff - ffmin) % ngpu);
+      SubFile &buf = e->bufs[2 * g + (e->used[g] & 1)];
+      if (e->used[g] >= 2 && slicer_wait_staging(e->h[g])) // the copy that last read this host buffer must be done
+        return fail_capi("slicer_wait_staging");
+      if (readSubFile(File + "." + std::to_string(ff), p.hydro, buf, true))
+        return 1;
+      const Header &data = buf.header;
+      if (!have_header)
+      {
+        first_header = data;
+        have_header = true;
+      }
+      if (buf.ntotal > e->capacity)
+      { // a larger sub-file than any seen so far: grow the device pools (rare; finishes pending work first)
+        if (e->used[0] || ff != ffmin)
+        {
+          std::cerr << "sub-file " << ff << " holds " << buf.ntotal << " particles, more than the engine's capacity " << e->capacity << std::endl;
+          return 1;
+        }
+        e->capacity = buf.ntotal + buf.ntotal / 8;
+        if (make_handles(e))
+          return 1;
+      }
+      if (myid == 0)
+        std::cout << " sub-file " << ff << ": " << buf.ntotal << " particles -> GPU " << e->devices[g] << std::endl;
+      int rc = e->used[g] == 0 ? slicer_begin_snapshot(e->h[g], data.boxsize, data.massarr, p.hydro) : slicer_next_batch(e->h[g]);
+      if (rc)
+        return fail_capi("slicer_begin_snapshot");
+      size_t off = 0;
+      for (int t = 0; t < 6; t++)
+      {
+        const size_t nt = (size_t)data.npart[t];
+        if (nt)
+        {
+          const bool pm = p.hydro && data.massarr[t] == 0;
+          if (slicer_stage_particles(e->h[g], t, buf.pos + 3 * off, SLICER_LAYOUT_AOS, pm ? buf.mass + off : nullptr, nt))
+            return fail_capi("slicer_stage_particles");
+        }
+        off += nt;
+      }
+      rc = e->used[g] == 0 ? slicer_deposit(e->h[g], descs.data(), nj) : slicer_deposit_accumulate(e->h[g], descs.data(), nj);
+      if (rc)
+        return fail_capi("slicer_deposit");
+      e->used[g]++;
+    }
+    for (int g = 0; g < ngpu; g++)
+      if (e->used[g] == 0)
+      { // a GPU without sub-files still contributes zero maps to the sum (slicer-v2.cpp:162-175: ranks with no files)
+        const double zero[6] = {0, 0, 0, 0, 0, 0};
+        if (slicer_begin_snapshot(e->h[g], have_header ? first_header.boxsize : 1.0, have_header ? first_header.massarr : zero, p.hydro) ||
+            slicer_deposit(e->h[g], descs.data(), nj))
+          return fail_capi("slicer_deposit");
+      }
+    if (ngpu > 1 && slicer_reduce_all(e->h.data(), ngpu, nj, 0)) // replaces the 7 MPI_Reduce of slicer-v2.cpp:214-217
+      return fail_capi("slicer_reduce_all");
+    for (int j = 0; j < nj; j++)
+    {
+      const int npix = jobs[j0 + j].npix;
+      long long counts[6];
+      mapxytot[j0 + j].resize((size_t)npix * npix);
+      if (slicer_fetch(e->h[0], j, -1, &mapxytot[j0 + j][0], counts, nullptr))
+        return fail_capi("slicer_fetch");
+      for (int t = 0; t < 6; t++)
+      {
+        ntotxyi[(size_t)(j0 + j) * 6 + t] = counts[t];
+        if (e->per_type)
+        {
+          mapxytoti[(size_t)(j0 + j) * 6 + t].resize((size_t)npix * npix);
+          if (slicer_fetch(e->h[0], j, t, &mapxytoti[(size_t)(j0 + j) * 6 + t][0], nullptr, nullptr))
+            return fail_capi("slicer_fetch");
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+int createDensityMaps(Engine *e, InputParams &p, Lens &lens, Random &random, int isnap, unsigned ffmin, unsigned ffmax,
+                      const std::string &File, double fovradiants, double rcase, std::valarray<float> &mapxytot,
+                      std::valarray<float> (&mapxytoti)[6], int (&ntotxyi)[6], int myid)
+{
+  std::vector<PlaneJob> jobs = {{isnap, rcase, p.npix}};
+  std::vector<std::valarray<float>> tot, per;
+  std::vector<long long> cnt;
+  if (createDensityMapsMulti(e, p, lens, random, jobs, ffmin, ffmax, File, fovradiants, tot, per, cnt, myid))
+    return 1;
+  mapxytot = tot[0];
+  for (int i = 0; i < 6; i++)
+  {
+    if (e->per_type)
+      mapxytoti[i] = per[i];
+    else
+      mapxytoti[i].resize((size_t)p.npix * p.npix); // zero-filled, as the reference's resize() leaves them
+    ntotxyi[i] = (int)cnt[i];
+  }
+  return 0;
+}
+
+static std::string plane_label(int pll)
+{ // slicer-v2.cpp:154-159
+  char b[32];
+  snprintf(b, sizeof(b), "%03d", pll);
+  return b;
+}
+
+int runLightCone(const std::string &inifile, const RunOptions &opt)
+{
+  const int myid = opt.quiet ? 1 : 0;
+  InputParams p;
+  if (readInput(p, inifile))
+    return 1;
+  if (p.simType == "SubFind")
+  {
+    std::cerr << "npix == 0 selects the SubFind halo catalogue branch, which this build does not provide" << std::endl;
+    return 1;
+  }
+  std::vector<std::string> snappath;
+  std::vector<double> snapred, snapbox;
+  if (readRedList(p.filredshiftlist, snapred, snappath, snapbox, p))
+    return 1;
+  Header simdata;
+  if (readHeader(p.pathsnap + snappath[0] + ".0", simdata))
+    return 1;
+  testHydro(p, simdata); // decided once from the first listed snapshot (slicer-v2.cpp:74-76)
+  CosmoTable cosmo;
+  cosmo.build(simdata.om0, simdata.oml, p.w, p.zs);
+  p.Ds = cosmo.getDl.eval(p.zs);
+  Lens lens;
+  if (buildPlanes(p, lens, snapred, snappath, snapbox, cosmo.getDl, cosmo.getZl, numberOfLensPerSnap, myid))
+    return 1;
+  double fovradiants = 0;
+  for (size_t i = 0; i < lens.ld.size(); i++)
+  {
+    if (i == 0)
+      lens.nrepperp.assign(lens.ld.size(), 0);
+    const double boxl = snapbox[lens.fromsnapi[i]] / 1e3 * POS_U;
+    if (!opt.replication)
+    {
+      if (testFov(p.fov, boxl, lens.ld2[i], 0, fovradiants))
+        return 1;
+    }
+    else
+      computeReplications(p.fov, boxl, lens.ld2[i], myid, fovradiants, lens.nrepperp[i]);
+  }
+  Random random;
+  randomizeBox(random, lens, p, numberOfLensPerSnap, 1, opt.fixed_vertex);
+
+  // per-plane rcase and npix, exactly as the sequential loop of slicer-v2.cpp:137-185 would see them
+  std::vector<double> rcase(lens.nplanes, 0.0);
+  std::vector<int> npix(lens.nplanes, p.npix);
+  float rc = 0.0f;
+  int npix_max = 1;
+  for (int isnap = 0; isnap < lens.nplanes; isnap++)
+  {
+    if (p.physical)
+      npix[isnap] = int((lens.ld2[isnap] + lens.ld[isnap]) / 2 * fovradiants / p.rgrid * 1e3 / POS_U) + 1;
+    if (lens.randomize[isnap])
+      rc = lens.ld[isnap] / snapbox[lens.fromsnapi[isnap]] * 1e3 / POS_U;
+    rcase[isnap] = rc;
+    npix_max = std::max(npix_max, npix[isnap]);
+  }
+  if (p.partinplanes && myid == 0)
+    std::cout << "!It is not possible to resume a Gadget run with partinplanes == true!" << std::endl
+              << "!!               Files on Output folder will be overwritten        !!" << std::endl;
+
+  Engine *e = nullptr;
+  int status = 0;
+  for (int s0 = 0; s0 < lens.nplanes && !status;)
+  {
+    // planes [s0, s1) use the same snapshot
+    int s1 = s0 + 1;
+    while (s1 < lens.nplanes && lens.fromsnapi[s1] == lens.fromsnapi[s0])
+      s1++;
+    std::vector<PlaneJob> jobs;
+    for (int isnap = s0; isnap < s1; isnap++)
+    {
+      if (!p.partinplanes && std::ifstream(fileOutput(p, plane_label(lens.pll[isnap]))))
+      { // resume: this plane was already written (slicer-v2.cpp:188-196)
+        if (myid == 0)
+          std::cout << fileOutput(p, plane_label(lens.pll[isnap])) << " Already exists" << std::endl;
+        continue;
+      }
+      jobs.push_back({isnap, rcase[isnap], npix[isnap]});
+    }
+    const std::string File = p.pathsnap + lens.fromsnap[s0];
+    Header snapdata;
+    if (readHeader(File + ".0", snapdata))
+    {
+      status = 1;
+      break;
+    }
+    if (!jobs.empty())
+    {
+      if (!e)
+      {
+        size_t tot = 0;
+        for (int i = 0; i < 6; i++)
+          tot += (size_t)snapdata.npartTotal[i] + ((size_t)(uint32_t)snapdata.nTotalHW[i] << 32);
+        const size_t cap = tot / std::max(1, snapdata.numfiles) * 5 / 4 + 65536;
+        e = engineCreate(opt.devices, npix_max, opt.mas, p.partinplanes, cap, opt.deposit_mode);
+        if (!e)
+        {
+          status = 1;
+          break;
+        }
+      }
+      std::vector<std::valarray<float>> tot, per;
+      std::vector<long long> cnt;
+      if (createDensityMapsMulti(e, p, lens, random, jobs, 0, snapdata.numfiles, File, fovradiants, tot, per, cnt, myid))
+      {
+        status = 1;
+        break;
+      }
+      for (size_t j = 0; j < jobs.size(); j++)
+      {
+        const int isnap = jobs[j].isnap;
+        const double zsim = cosmo.getZl.eval((lens.ld2[isnap] + lens.ld[isnap]) / 2.0);
+        InputParams pj = p;
+        pj.npix = jobs[j].npix;
+        try
+        {
+          writeMaps(pj, snapdata, lens, isnap, zsim, plane_label(lens.pll[isnap]), tot[j], p.partinplanes ? &per[j * 6] : nullptr, &cnt[j * 6], 0);
+        }
+        catch (const SliceError &err)
+        {
+          std::cerr << "It was not possible to create the map: " << err.what << std::endl;
+          status = 1;
+          break;
+        }
+      }
+    }
+    s0 = s1;
+  }
+  engineDestroy(e);
+  return status;
+}
+
+} // namespace slicer
