@@ -273,7 +273,7 @@ int runLightCone(const std::string &inifile, const RunOptions &opt)
   cosmo.build(simdata.om0, simdata.oml, p.w, p.zs);
   p.Ds = cosmo.getDl.eval(p.zs);
   Lens lens;
-  if (buildPlanes(p, lens, snapred, snappath, snapbox, cosmo.getDl, cosmo.getZl, numberOfLensPerSnap, myid))
+  if (buildPlanes(p, lens, snapred, snappath, snapbox, cosmo.getDl, cosmo.getZl, numberOfLensPerSnap, 0)) // rank 0 writes planes_list
     return 1;
   double fovradiants = 0;
   for (size_t i = 0; i < lens.ld.size(); i++)
