@@ -251,7 +251,8 @@ def ours(args, rank, world, local_rank):
     massarr = [0, MASS, 0, 0, 0, 0]
 
     # ------------------------------------------------------------------ resident phase: `value` and the roofline
-    s = capi.Slicer(npix_max=NPIX, max_planes=LENS_PER_SNAP, mas=capi.MAS_TSC, particle_capacity=npart + 64, device=local_rank)
+    s = capi.Slicer(npix_max=NPIX, max_planes=LENS_PER_SNAP, mas=capi.MAS_TSC, particle_capacity=npart + 64, device=local_rank,
+                    deposit_mode=args.deposit_mode)
     if world > 1:
         uid = [capi.Slicer.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -287,8 +288,14 @@ def ours(args, rank, world, local_rank):
         sampler.stop()
         clocks = sampler.summary(t0, t1)
     value = world * npart * args.steps / (ms * 1e-3)
-    kernel_ms = st.deposit_ms_sum / max(1, st.deposit_launches)
+    kernel_ms = st.deposit_ms_sum / max(1, st.deposit_passes)
     launches = int(st.launches)
+    # per-group pass time (one extra pass each, outside the timed region): shows the near/far spread behind the average
+    per_group = []
+    for g in range(NGROUPS):
+        s.deposit(groups[g])
+        per_group.append(round(s.stats().last_deposit_ms, 3))
+    s.deposit(groups[(args.steps - 1) % NGROUPS])
     accepted = []
     for k in range(LENS_PER_SNAP):
         _, c, _ = s.fetch(k, -1, NPIX, want_map=False)
@@ -301,7 +308,8 @@ def ours(args, rank, world, local_rank):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = 12.0 * npart / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "pipe::deposit_pipelined_kernel<TSC,AOS>", "kernel_ms": kernel_ms,
+                "traffic": None, "kernel": "one pass = pipe::deposit_pipelined_kernel<TSC,AOS,SINGLE,*> (stream + screen + exact projection) "
+                "[+ binned::bin_* sort + binned::tile_deposit_kernel when > 1 % of the snapshot is inside the field]", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": 12 * npart, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else
                 "fallback 6650 GB/s"}
     prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
@@ -320,7 +328,7 @@ def ours(args, rank, world, local_rank):
         capi._check(capi.lib().slicer_download_segment(s.h, 0, ctypes.c_void_p(pin.ptr), None))  # same particles, now on the host
         s.close()
         e = capi.Slicer(npix_max=NPIX, max_planes=LENS_PER_SNAP, mas=capi.MAS_TSC, particle_capacity=per + 64, staging_buffers=2,
-                        device=local_rank)
+                        device=local_rank, deposit_mode=args.deposit_mode)
         if world > 1:
             uid = [capi.Slicer.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
@@ -381,7 +389,7 @@ def ours(args, rank, world, local_rank):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64->int64",
             "data": "synthetic", "config": workload_config(world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks,
-            "extra": {"stream_rate_particles_per_s": value, "ref_equiv_particle_passes_per_s": value * LENS_PER_SNAP,
+            "extra": {"per_group_kernel_ms": per_group, "stream_rate_particles_per_s": value, "ref_equiv_particle_passes_per_s": value * LENS_PER_SNAP,
                       "accepted_pairs_last_step": accepted, "kernel_ms_avg": kernel_ms,
                       "gpu_launches_e2e": launches_e2e if e2e else None},
         }
@@ -398,6 +406,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--deposit-mode", type=int, default=0, help="0 auto, 1 direct map atomics, 2 binned shared-memory tiles")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1,0 +1,63 @@
+"""world_size-2 gloo tests (CPU) of the multi-rank host logic: unique-id hand-out, sub-file split, max-over-ranks timing,
+and the property the multi-GPU path relies on: sharded int64 fixed-point planes sum to the unsharded plane exactly,
+whatever the split (the reference's float MPI_Reduce does not have this property)."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from slicer_b200 import dist as sdist
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        uid = sdist.broadcast_unique_id(lambda: bytes(range(128)), rank)
+        t = sdist.max_over_ranks(1.0 + rank)
+        # every rank deposits its shard of the accepted particles with the oracle's fixed-point accumulator
+        import sys
+
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        from oracle.oracle_bindings import Oracle
+
+        orc = Oracle()
+        rng = np.random.default_rng(5)
+        n, nn = 20000, 32
+        xs, ys = rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32)
+        ms = (rng.random(n) * 3).astype(np.float32)
+        mine = sdist.balanced_subfiles(n, world, rank)
+        part = orc.gridist_w_fixed(xs[mine], ys[mine], ms[mine], nn, 40)
+        total = sdist.sum_int64_planes(part)
+        if rank == 0:
+            full = orc.gridist_w_fixed(xs, ys, ms, nn, 40)
+            q.put(dict(uid_ok=uid == bytes(range(128)), tmax=t, exact=bool(np.array_equal(total.numpy(), full))))
+        else:
+            q.put(dict(uid_ok=uid == bytes(range(128)), tmax=t))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_plumbing():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r["uid_ok"] for r in res) and all(r["tmax"] == 2.0 for r in res)
+    assert any(r.get("exact") for r in res)
+
+
+def test_subfile_split_matches_reference():
+    # slicer-v2.cpp:162-175
+    assert [sdist.subfile_range(10, 4, r) for r in range(4)] == [(0, 2), (2, 4), (4, 6), (6, 10)]
+    assert [sdist.subfile_range(2, 4, r) for r in range(4)] == [(0, 0), (0, 0), (0, 0), (0, 2)]  # only the last rank works
+    assert sorted(sum((sdist.balanced_subfiles(10, 4, r) for r in range(4)), [])) == list(range(10))
