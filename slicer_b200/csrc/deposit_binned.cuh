@@ -22,13 +22,18 @@
 namespace binned
 {
 
-constexpr int TILE = 116;          // interior cells per tile side
+#ifndef SLICER_TILE
+#define SLICER_TILE 116
+#endif
+#ifndef SLICER_TILE_CTAS
+#define SLICER_TILE_CTAS 2
+#endif
+constexpr int TILE = SLICER_TILE;  // interior cells per tile side (116: two CTAs per SM; 166: one)
 constexpr int TW = TILE + 2;       // + 1-cell halo for the 3x3 stencil
 constexpr int TCELLS = TW * TW;    // 13,924 cells x 8 B = 111,392 B: two CTAs per SM
 constexpr int MAX_BINS = 2048;     // planes x tiles^2 per pass
-constexpr int SCATTER_BATCH = 32768;
 constexpr int SCATTER_THREADS = 512;
-constexpr int DEPOSIT_THREADS = 512;
+constexpr int DEPOSIT_THREADS = 1024 / SLICER_TILE_CTAS;
 
 struct EmitDev
 {
@@ -81,7 +86,6 @@ __device__ __forceinline__ void for_each_key(const unsigned short *key, unsigned
     f(i, (unsigned)key[i]);
 }
 
-constexpr int SORT_UNROLL = 8; // records in flight per thread in the sort kernels
 
 // K2a: one CTA per region: shared-memory histogram of its keys -> region_hist[bin][region]
 __global__ void __launch_bounds__(SCATTER_THREADS) bin_histogram_kernel(const __grid_constant__ SortDev D)
@@ -173,52 +177,137 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
 }
 
 // K2d: one CTA per region: record -> bin_start[bin] + (offset of this region in the bin) + (rank inside the region).
-// No global atomics; SORT_UNROLL coalesced (key, record) loads in flight per thread before the ranks are taken.
-__global__ void __launch_bounds__(SCATTER_THREADS) bin_scatter_kernel(const __grid_constant__ SortDev D)
+// Measured on B200: a warp store whose 32 lanes hit 32 different sectors costs ~3-6 cycles per LANE per SM
+// (~50-100 G sector requests/s chip-wide, whatever the instruction: st, st.cs, red), 5x more than the same bytes
+// written as full sectors.  So every batch of SCATTER_BATCH records is first counting-sorted in shared memory and
+// then written out in sorted order: consecutive lanes carry consecutive records of one bin, i.e. consecutive
+// addresses.  No global atomics; the bin layout is deterministic up to the order inside a (batch, bin) run.
+constexpr int SCATTER_BATCH = 8192;
+constexpr int SCATTER_PER = SCATTER_BATCH / SCATTER_THREADS; // records per thread per batch
+struct ScatterSmem
 {
-  __shared__ unsigned cur[MAX_BINS];
+  float2 rec[SCATTER_BATCH];
+  float mass[SCATTER_BATCH];
+  unsigned short bin[SCATTER_BATCH];
+  unsigned cnt[MAX_BINS];    // records of the batch per bin, then running rank
+  unsigned lstart[MAX_BINS]; // first sorted slot of the bin in this batch
+  unsigned gcur[MAX_BINS];   // next free global slot of the bin for this region
+  unsigned wsum[SCATTER_THREADS / 32];
+};
+
+__global__ void __launch_bounds__(SCATTER_THREADS, 2) bin_scatter_kernel(const __grid_constant__ SortDev D)
+{
+  extern __shared__ __align__(16) unsigned char scatter_raw[];
+  ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(scatter_raw);
+  constexpr int PER = MAX_BINS / SCATTER_THREADS; // bins per thread in the scan
   const int r = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const unsigned n = D.region_count[r];
   if (n == 0)
     return;
-  for (int i = threadIdx.x; i < D.nbins; i += SCATTER_THREADS)
-    cur[i] = D.bin_start[i] + D.region_hist[(size_t)i * D.nregions + r];
-  __syncthreads();
+  for (int i = t; i < MAX_BINS; i += SCATTER_THREADS)
+    sm.gcur[i] = i < D.nbins ? D.bin_start[i] + D.region_hist[(size_t)i * D.nregions + r] : 0u;
   const unsigned long long off = (unsigned long long)r * D.region_cap;
   const unsigned short *key = D.key_u + off;
   const float2 *rec = D.rec_u + off;
   const float *mass = D.mass_u ? D.mass_u + off : nullptr;
-  for (unsigned base = 0; base < n; base += SCATTER_THREADS * SORT_UNROLL)
+  for (unsigned base = 0; base < n; base += SCATTER_BATCH)
   {
-    unsigned k[SORT_UNROLL];
-    float2 e[SORT_UNROLL];
-    float m[SORT_UNROLL];
+    const unsigned nb = min(n - base, (unsigned)SCATTER_BATCH);
+    for (int i = t; i < MAX_BINS; i += SCATTER_THREADS)
+      sm.cnt[i] = 0;
+    __syncthreads();
+    // 1. coalesced loads, rank inside (batch, bin)
+    unsigned k[SCATTER_PER]; // bin | rank << 16 (rank < SCATTER_BATCH = 2^13)
+    float2 e[SCATTER_PER];
 #pragma unroll
-    for (int j = 0; j < SORT_UNROLL; j++)
+    for (int j = 0; j < SCATTER_PER; j++)
     {
-      const unsigned i = base + j * SCATTER_THREADS + threadIdx.x;
+      const unsigned i = j * SCATTER_THREADS + t;
       k[j] = 0xffffffffu;
-      if (i < n)
+      if (i < nb)
       {
-        k[j] = key[i];
-        e[j] = rec[i];
-        m[j] = mass ? mass[i] : 0.f;
+        k[j] = key[base + i];
+        e[j] = rec[base + i];
       }
     }
 #pragma unroll
-    for (int j = 0; j < SORT_UNROLL; j++)
+    for (int j = 0; j < SCATTER_PER; j++)
+      if (k[j] != 0xffffffffu)
+        k[j] |= atomicAdd(&sm.cnt[k[j]], 1u) << 16;
+    __syncthreads();
+    // 2. exclusive scan of the batch histogram: thread t owns bins [PER t, PER t + PER)
+    unsigned c[PER], x = 0;
+#pragma unroll
+    for (int j = 0; j < PER; j++)
+    {
+      c[j] = sm.cnt[PER * t + j];
+      x += c[j];
+    }
+    unsigned incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1)
+    {
+      const unsigned y = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d)
+        incl += y;
+    }
+    if (lane == 31)
+      sm.wsum[w] = incl;
+    __syncthreads();
+    if (w == 0)
+    {
+      const unsigned sv = lane < SCATTER_THREADS / 32 ? sm.wsum[lane] : 0u;
+      unsigned si = sv;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1)
+      {
+        const unsigned y = __shfl_up_sync(0xffffffffu, si, d);
+        if (lane >= d)
+          si += y;
+      }
+      if (lane < SCATTER_THREADS / 32)
+        sm.wsum[lane] = si - sv;
+    }
+    __syncthreads();
+    unsigned ex = sm.wsum[w] + incl - x;
+#pragma unroll
+    for (int j = 0; j < PER; j++)
+    {
+      sm.lstart[PER * t + j] = ex;
+      ex += c[j];
+    }
+    __syncthreads();
+    // 3. sorted order in shared memory
+#pragma unroll
+    for (int j = 0; j < SCATTER_PER; j++)
       if (k[j] != 0xffffffffu)
       {
-        const unsigned pos = atomicAdd(&cur[k[j]], 1u);
-        D.rec_s[pos] = e[j];
+        const unsigned lp = sm.lstart[k[j] & 0xffffu] + (k[j] >> 16);
+        sm.rec[lp] = e[j];
+        sm.bin[lp] = (unsigned short)(k[j] & 0xffffu);
         if (mass)
-          D.mass_s[pos] = m[j];
+          sm.mass[lp] = mass[base + j * SCATTER_THREADS + t];
       }
+    __syncthreads();
+    // 4. write-out: slot i of the sorted batch -> gcur[bin] + (i - lstart[bin]); runs are contiguous in memory
+    for (unsigned i = t; i < nb; i += SCATTER_THREADS)
+    {
+      const unsigned b = sm.bin[i];
+      const unsigned dst = sm.gcur[b] + (i - sm.lstart[b]);
+      D.rec_s[dst] = sm.rec[i];
+      if (mass)
+        D.mass_s[dst] = sm.mass[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; j++)
+      sm.gcur[PER * t + j] += c[j];
   }
 }
 
 // K3: one CTA per (plane, tile) bin
-__global__ void __launch_bounds__(DEPOSIT_THREADS, 2)
+__global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
     tile_deposit_kernel(const __grid_constant__ PassParams P, const __grid_constant__ SortDev D, int ntile, int type, float const_mass)
 {
   extern __shared__ __align__(16) unsigned tile_smem[];

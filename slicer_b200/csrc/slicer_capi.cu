@@ -820,8 +820,9 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
     binned::bin_histogram_kernel<<<nregions, binned::SCATTER_THREADS, 0, h->compute>>>(Q);
     binned::bin_region_scan_kernel<<<nbins, 1024, 0, h->compute>>>(Q);
     binned::bin_scan_kernel<<<1, 1024, 0, h->compute>>>(Q);
-    binned::bin_scatter_kernel<<<nregions, binned::SCATTER_THREADS, 0, h->compute>>>(Q);
-    binned::tile_deposit_kernel<<<nbins, binned::DEPOSIT_THREADS, binned::TCELLS * 8, h->compute>>>(P, Q, nt, D.type, D.const_mass);
+    binned::bin_scatter_kernel<<<nregions, binned::SCATTER_THREADS, sizeof(binned::ScatterSmem), h->compute>>>(Q);
+    if (!(h->debug & 4)) // measurement aid: SLICER_B200_DEBUG bit 2 skips the tile deposit
+      binned::tile_deposit_kernel<<<nbins, binned::DEPOSIT_THREADS, binned::TCELLS * 8, h->compute>>>(P, Q, nt, D.type, D.const_mass);
     CU(cudaGetLastError());
     h->stats.launches += 5;
   }
