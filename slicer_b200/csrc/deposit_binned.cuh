@@ -354,33 +354,35 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
       wy[k] = __fmul_rn(sm, vy);
     }
     const int lx = gx - 1 - x0, ly = gy - 1 - y0; // local index of stencil cell (0,0)
-    const bool interior = gx >= 1 && gx <= nn - 2 && gy >= 1 && gy <= nn - 2;
-#pragma unroll
-    for (int jy = 0; jy < 3; jy++)
+    unsigned *plo = lo + ly * TW + lx, *phi = hi + ly * TW + lx;
+    if (gx >= 1 && gx <= nn - 2 && gy >= 1 && gy <= nn - 2)
     {
+      // interior stencil (all but the map's border): nine unconditional limb pairs, no branches — adding a zero
+      // limb is harmless and cheaper than testing for it
 #pragma unroll
-      for (int jx = 0; jx < 3; jx++)
-      {
-        if (!interior)
+      for (int jy = 0; jy < 3; jy++)
+#pragma unroll
+        for (int jx = 0; jx < 3; jx++)
+        {
+          const unsigned long long v = (unsigned long long)chain::to_fixed(__fmul_rn(wx[jx], wy[jy]), L);
+          const unsigned vl = (unsigned)v, vh = (unsigned)(v >> 32);
+          const unsigned old = atomicAdd(plo + jy * TW + jx, vl);
+          atomicAdd(phi + jy * TW + jx, vh + ((old + vl < old) ? 1u : 0u));
+        }
+    }
+    else
+    {
+      for (int jy = 0; jy < 3; jy++)
+        for (int jx = 0; jx < 3; jx++)
         {
           const int cx = gx + jx - 1, cy = gy + jy - 1;
           if (cx < 0 || cx >= nn || cy < 0 || cy >= nn)
             continue; // utilities.cpp:91 drops cells outside the map
+          const unsigned long long v = (unsigned long long)chain::to_fixed(__fmul_rn(wx[jx], wy[jy]), L);
+          const unsigned vl = (unsigned)v, vh = (unsigned)(v >> 32);
+          const unsigned old = atomicAdd(plo + jy * TW + jx, vl);
+          atomicAdd(phi + jy * TW + jx, vh + ((old + vl < old) ? 1u : 0u));
         }
-        const unsigned long long v = (unsigned long long)chain::to_fixed(__fmul_rn(wx[jx], wy[jy]), L);
-        if (!v)
-          continue;
-        const int c = (ly + jy) * TW + lx + jx;
-        const unsigned vl = (unsigned)v, vh = (unsigned)(v >> 32);
-        unsigned carry = 0;
-        if (vl)
-        {
-          const unsigned old = atomicAdd(&lo[c], vl);
-          carry = (old + vl < old) ? 1u : 0u;
-        }
-        if (vh + carry)
-          atomicAdd(&hi[c], vh + carry);
-      }
     }
   };
   {

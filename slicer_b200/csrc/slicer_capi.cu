@@ -715,6 +715,9 @@ static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int npl
     X.raw_hi = float_floor(h->boxsize * (1.0 - 1e-6)); // 0 < raw < raw_hi  =>  raw/box in (0,1): no wrap at the first site
   }
   P->pair = P->fast && P->pl[0].nt > 0;
+  for (int t = 0; t < P->nxform; t++)
+    if (!P->xf[t].exact_f32)
+      P->pair = 0; // the pair paths assume a float-exact box and centre
   for (int q = 1; q < P->nplanes; q++)
     if (P->pl[q].T != P->pl[0].T || P->pl[q].fovrad != P->pl[0].fovrad || P->pl[q].npix != P->pl[0].npix)
       P->pair = 0;
