@@ -32,7 +32,7 @@ constexpr int TILE = SLICER_TILE;  // interior cells per tile side (116: two CTA
 constexpr int TW = TILE + 2;       // + 1-cell halo for the 3x3 stencil
 constexpr int TCELLS = TW * TW;    // 13,924 cells x 8 B = 111,392 B: two CTAs per SM
 constexpr int MAX_BINS = 2048;     // planes x tiles^2 per pass
-constexpr int SCATTER_THREADS = 512;
+constexpr int SCATTER_THREADS = 1024;
 constexpr int DEPOSIT_THREADS = 1024 / SLICER_TILE_CTAS;
 
 struct EmitDev
@@ -182,12 +182,11 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
 // written as full sectors.  So every batch of SCATTER_BATCH records is first counting-sorted in shared memory and
 // then written out in sorted order: consecutive lanes carry consecutive records of one bin, i.e. consecutive
 // addresses.  No global atomics; the bin layout is deterministic up to the order inside a (batch, bin) run.
-constexpr int SCATTER_BATCH = 8192;
+constexpr int SCATTER_BATCH = 16384;
 constexpr int SCATTER_PER = SCATTER_BATCH / SCATTER_THREADS; // records per thread per batch
 struct ScatterSmem
 {
   float2 rec[SCATTER_BATCH];
-  float mass[SCATTER_BATCH];
   unsigned short bin[SCATTER_BATCH];
   unsigned cnt[MAX_BINS];    // records of the batch per bin, then running rank
   unsigned lstart[MAX_BINS]; // first sorted slot of the bin in this batch
@@ -195,10 +194,11 @@ struct ScatterSmem
   unsigned wsum[SCATTER_THREADS / 32];
 };
 
-__global__ void __launch_bounds__(SCATTER_THREADS, 2) bin_scatter_kernel(const __grid_constant__ SortDev D)
+__global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const __grid_constant__ SortDev D)
 {
   extern __shared__ __align__(16) unsigned char scatter_raw[];
   ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(scatter_raw);
+  float *smass = reinterpret_cast<float *>(sm.rec); // per-particle masses reuse the record staging in a second sweep
   constexpr int PER = MAX_BINS / SCATTER_THREADS; // bins per thread in the scan
   const int r = blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
@@ -286,8 +286,6 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 2) bin_scatter_kernel(const _
         const unsigned lp = sm.lstart[k[j] & 0xffffu] + (k[j] >> 16);
         sm.rec[lp] = e[j];
         sm.bin[lp] = (unsigned short)(k[j] & 0xffffu);
-        if (mass)
-          sm.mass[lp] = mass[base + j * SCATTER_THREADS + t];
       }
     __syncthreads();
     // 4. write-out: slot i of the sorted batch -> gcur[bin] + (i - lstart[bin]); runs are contiguous in memory
@@ -296,10 +294,22 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 2) bin_scatter_kernel(const _
       const unsigned b = sm.bin[i];
       const unsigned dst = sm.gcur[b] + (i - sm.lstart[b]);
       D.rec_s[dst] = sm.rec[i];
-      if (mass)
-        D.mass_s[dst] = sm.mass[i];
     }
     __syncthreads();
+    if (mass)
+    { // same permutation for the masses
+#pragma unroll
+      for (int j = 0; j < SCATTER_PER; j++)
+        if (k[j] != 0xffffffffu)
+          smass[sm.lstart[k[j] & 0xffffu] + (k[j] >> 16)] = mass[base + j * SCATTER_THREADS + t];
+      __syncthreads();
+      for (unsigned i = t; i < nb; i += SCATTER_THREADS)
+      {
+        const unsigned b = sm.bin[i];
+        D.mass_s[sm.gcur[b] + (i - sm.lstart[b])] = smass[i];
+      }
+      __syncthreads();
+    }
 #pragma unroll
     for (int j = 0; j < PER; j++)
       sm.gcur[PER * t + j] += c[j];

@@ -645,7 +645,6 @@ static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int npl
       L.pow2 = (d.npix & (d.npix - 1)) == 0;
       L.T = d.fovradiants * (1. + 2. / d.npix) * 0.5; /* densitymaps.cpp:383 */
       L.fovrad = d.fovradiants;
-      L.inv_fov = 1.0 / d.fovradiants;
       L.dl = 1. / double(d.npix);  /* utilities.cpp:50 */
       L.half_dl = 0.5 * L.dl;      /* utilities.cpp:9  */
       L.onehalf_dl = 0.5 * 3.0 * L.dl; /* utilities.cpp:11 */
