@@ -23,15 +23,15 @@ namespace binned
 {
 
 #ifndef SLICER_TILE
-#define SLICER_TILE 116
+#define SLICER_TILE 166
 #endif
 #ifndef SLICER_TILE_CTAS
-#define SLICER_TILE_CTAS 2
+#define SLICER_TILE_CTAS 1
 #endif
-constexpr int TILE = SLICER_TILE;  // interior cells per tile side (116: two CTAs per SM; 166: one)
+constexpr int TILE = SLICER_TILE;  // interior cells per tile side (166: one 1024-thread CTA per SM owns 226 KB; 116: two CTAs)
 constexpr int TW = TILE + 2;       // + 1-cell halo for the 3x3 stencil
-constexpr int TCELLS = TW * TW;    // 13,924 cells x 8 B = 111,392 B: two CTAs per SM
-constexpr int MAX_BINS = 2048;     // planes x tiles^2 per pass
+constexpr int TCELLS = TW * TW;    // 28,224 cells x 8 B = 225,792 B of shared memory
+constexpr int MAX_BINS = 4096;     // planes x tiles^2 per pass (4 planes of 4096^2, 16 planes of 2048^2)
 constexpr int SCATTER_THREADS = 1024;
 constexpr int DEPOSIT_THREADS = 1024 / SLICER_TILE_CTAS;
 
@@ -159,19 +159,28 @@ __global__ void __launch_bounds__(1024) bin_region_scan_kernel(const __grid_cons
     D.bin_count[blockIdx.x] = carry;
 }
 
-// K2c: exclusive scan of <= MAX_BINS bin totals (one CTA)
+// K2c: exclusive scan of <= MAX_BINS bin totals (one CTA; thread t owns bins [PER t, PER t + PER))
 __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ SortDev D)
 {
   __shared__ unsigned wsum[32];
   __shared__ unsigned total;
+  constexpr int PER = MAX_BINS / 1024;
   const int t = threadIdx.x;
-  const unsigned v0 = (2 * t < D.nbins) ? D.bin_count[2 * t] : 0u;
-  const unsigned v1 = (2 * t + 1 < D.nbins) ? D.bin_count[2 * t + 1] : 0u;
-  const unsigned excl = block_exclusive_scan_1024(v0 + v1, wsum, &total);
-  if (2 * t < D.nbins)
-    D.bin_start[2 * t] = excl;
-  if (2 * t + 1 < D.nbins)
-    D.bin_start[2 * t + 1] = excl + v0;
+  unsigned v[PER], x = 0;
+#pragma unroll
+  for (int j = 0; j < PER; j++)
+  {
+    v[j] = (PER * t + j < D.nbins) ? D.bin_count[PER * t + j] : 0u;
+    x += v[j];
+  }
+  unsigned excl = block_exclusive_scan_1024(x, wsum, &total);
+#pragma unroll
+  for (int j = 0; j < PER; j++)
+  {
+    if (PER * t + j < D.nbins)
+      D.bin_start[PER * t + j] = excl;
+    excl += v[j];
+  }
   if (t == 0)
     D.bin_start[D.nbins] = total;
 }
@@ -205,8 +214,8 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
   const unsigned n = D.region_count[r];
   if (n == 0)
     return;
-  for (int i = t; i < MAX_BINS; i += SCATTER_THREADS)
-    sm.gcur[i] = i < D.nbins ? D.bin_start[i] + D.region_hist[(size_t)i * D.nregions + r] : 0u;
+  for (int i = t; i < D.nbins; i += SCATTER_THREADS)
+    sm.gcur[i] = D.bin_start[i] + D.region_hist[(size_t)i * D.nregions + r];
   const unsigned long long off = (unsigned long long)r * D.region_cap;
   const unsigned short *key = D.key_u + off;
   const float2 *rec = D.rec_u + off;
@@ -214,8 +223,8 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
   for (unsigned base = 0; base < n; base += SCATTER_BATCH)
   {
     const unsigned nb = min(n - base, (unsigned)SCATTER_BATCH);
-    for (int i = t; i < MAX_BINS; i += SCATTER_THREADS)
-      sm.cnt[i] = 0;
+    for (int i = t; i < D.nbins; i += SCATTER_THREADS)
+      sm.cnt[i] = 0; // bins >= nbins hold garbage: it only reaches prefix sums of bins that do not exist
     __syncthreads();
     // 1. coalesced loads, rank inside (batch, bin)
     unsigned k[SCATTER_PER]; // bin | rank << 16 (rank < SCATTER_BATCH = 2^13)

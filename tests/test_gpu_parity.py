@@ -256,3 +256,26 @@ def test_binned_multi_plane_multi_xform(oracle):
             res = oracle.plane_from_particles(types, p, npix, frac_bits=fb)
             assert counts[k].tolist() == res["counts"].tolist()
             assert np.array_equal(fixed[mode][k], res["fixed"][1]), (mode, k)
+
+
+def test_binned_deposit_large_map(oracle):
+    """4096^2 map, two planes: 1250 (plane, tile) bins; records, sort and tiles agree with the oracle bit for bit."""
+    box = 128000.0
+    n = 250000
+    pos = synth.uniform_positions(n, box, 41)
+    types = [dict(type=1, raw=pos, const_mass=2.25)]
+    npix = 4096
+    fov = 0.7
+    planes = [dict(boxsize=box, sgn=[1, 1, -1], face=6, centre=[0.5, 0.25, 0.75], rcase=1.0, ld=128.0 + 32.0 * k, ld2=128.0 + 32.0 * (k + 1),
+                   nrepperp=0, fovradiants=fov) for k in range(2)]
+    descs = [capi.plane_desc(p["sgn"], p["face"], p["centre"], p["rcase"], p["ld"], p["ld2"], fov, npix) for p in planes]
+    with capi.Slicer(npix_max=npix, max_planes=2, mas=capi.MAS_TSC, particle_capacity=n + 64, deposit_mode=capi.DEPOSIT_BINNED) as s:
+        s.begin_snapshot(box, [0, 2.25, 0, 0, 0, 0], False)
+        s.stage(1, pos)
+        s.deposit(descs)
+        fb = s.frac_bits
+        for k, p in enumerate(planes):
+            res = oracle.plane_from_particles(types, p, npix, frac_bits=fb)
+            _, counts, ingrid = s.fetch(k, -1, npix, want_map=False)
+            assert counts.tolist() == res["counts"].tolist() and counts[1] > 20000
+            assert np.array_equal(s.fetch_fixed(k, -1, npix).reshape(-1), res["fixed"][1])
