@@ -30,6 +30,19 @@ def build(force: bool = False) -> str:
     return LIB_PATH
 
 
+_libc = C.CDLL("libc.so.6")
+_libc.srand.argtypes = [C.c_uint]
+_libc.rand.restype = C.c_int
+
+
+def libc_srand(seed: int) -> None:
+    _libc.srand(C.c_uint(seed & 0xFFFFFFFF))
+
+
+def libc_rand() -> int:
+    return _libc.rand()
+
+
 class Oracle:
     def __init__(self):
         build()
@@ -69,20 +82,22 @@ class Oracle:
         return np.float32(self.lib.orc_weight(float(np.float32(ixx)), float(np.float32(ixh)), float(dx)))
 
     def select_project(self, x, y, z, ld, ld2, boxsize, nrepperp, fovradiants, npix, const_mass=1.0,
-                       per_particle=None, max_m=MAX_M, snopt=0):
+                       per_particle=None, max_m=MAX_M, snopt=0, cap=None):
         n = len(x)
-        cap = max(1024, n // 4)
+        cap = cap or max(1024, n // 4)
         pp = None
         if per_particle is not None:
             per_particle = np.ascontiguousarray(per_particle, np.float32)
             pp = per_particle.ctypes.data
         while True:
             xs, ys, ms = (np.empty(cap, np.float32) for _ in range(3))
-            if snopt:
-                raise NotImplementedError("call select_project with snopt only after seeding libc rand explicitly")
+            # snopt > 0 consumes libc rand() (one per accepted pair): the caller seeds it (libc_srand) and, because a
+            # too-small buffer forces a second call, must give a `cap` that is large enough (checked below)
             na = self.lib.orc_select_project(x, y, z, pp, float(np.float32(const_mass)), float(max_m), n, float(ld),
                                              float(ld2), float(boxsize), int(nrepperp), float(fovradiants), int(npix),
-                                             0, xs, ys, ms, cap)
+                                             int(snopt), xs, ys, ms, cap)
+            if snopt and na > cap:
+                raise RuntimeError("select_project(snopt>0): pass cap >= number of accepted pairs")
             if na <= cap:
                 return xs[:na].copy(), ys[:na].copy(), ms[:na].copy()
             cap = int(na)

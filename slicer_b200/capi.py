@@ -82,7 +82,7 @@ EXPORTS = [
     "slicer_stage_synthetic", "slicer_download_segment", "slicer_deposit", "slicer_deposit_accumulate",
     "slicer_reduce", "slicer_fetch", "slicer_fetch_fixed", "slicer_synchronize", "slicer_get_stats",
     "slicer_frac_bits", "slicer_comm_unique_id", "slicer_comm_init_rank", "slicer_comm_init_all",
-    "slicer_reduce_all", "slicer_wait_staging", "slicer_reset_stats", "slicer_timer_begin", "slicer_timer_end",
+    "slicer_reduce_all", "slicer_wait_staging", "slicer_count_accepted", "slicer_deposit_degraded", "slicer_reset_stats", "slicer_timer_begin", "slicer_timer_end",
 ]
 
 
@@ -125,6 +125,8 @@ def lib() -> C.CDLL:
     L.slicer_deposit.argtypes = [C.c_void_p, C.POINTER(PlaneDesc), C.c_int]
     L.slicer_deposit_accumulate.argtypes = [C.c_void_p, C.POINTER(PlaneDesc), C.c_int]
     L.slicer_reduce.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.slicer_count_accepted.argtypes = [C.c_void_p, C.POINTER(PlaneDesc), C.c_int, C.c_void_p]
+    L.slicer_deposit_degraded.argtypes = [C.c_void_p, C.POINTER(PlaneDesc), C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int]
     L.slicer_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.slicer_fetch_fixed.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     L.slicer_synchronize.argtypes = [C.c_void_p]
@@ -283,6 +285,20 @@ class Slicer:
         arr = planes if isinstance(planes, C.Array) else self._array(planes)
         fn = lib().slicer_deposit_accumulate if accumulate else lib().slicer_deposit
         _check(fn(self.h, arr, len(arr)))
+
+    def count_accepted(self, planes: Sequence[PlaneDesc]) -> np.ndarray:
+        """-> int64 [nplanes, 6]: accepted (particle, replica) pairs of the resident batch per plane and type."""
+        arr = planes if isinstance(planes, C.Array) else self._array(planes)
+        out = np.zeros((len(arr), 6), np.int64)
+        _check(lib().slicer_count_accepted(self.h, arr, len(arr), out.ctypes.data))
+        return out
+
+    def deposit_degraded(self, planes: Sequence[PlaneDesc], snopt: int, keep: Sequence[np.ndarray], accumulate: bool = False):
+        """keep[q]: uint8, one entry per accepted pair of plane q in the reference's order (after count_accepted)."""
+        arr = planes if isinstance(planes, C.Array) else self._array(planes)
+        keep = [np.ascontiguousarray(k, np.uint8) for k in keep]
+        ptrs = (C.c_void_p * len(arr))(*[k.ctypes.data if k.size else None for k in keep])
+        _check(lib().slicer_deposit_degraded(self.h, arr, len(arr), int(snopt), ptrs, int(accumulate)))
 
     def reduce(self, nplanes: int, root: int = 0):
         _check(lib().slicer_reduce(self.h, nplanes, root))

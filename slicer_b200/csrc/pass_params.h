@@ -57,6 +57,7 @@ struct PlaneDev
   unsigned long long *acc;    // this plane's accumulators: [ntypes_alloc][npix*npix] int64 fixed point
   unsigned long long *counts; // [SLICER_NTYPES][2]: accepted pairs, in-grid pairs
   unsigned long long type_stride; // npix*npix when per-type maps are kept, else 0
+  int slot;                       // the caller's plane index (device slots are grouped by randomisation)
 };
 
 struct PassParams

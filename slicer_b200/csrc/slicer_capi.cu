@@ -18,6 +18,7 @@
 #include "aux_kernels.cuh"
 #include "deposit_simple.cuh"
 #include "deposit_pipelined.cuh"
+#include "deposit_degrade.cuh"
 
 #define POS_U 1.0 /* gadget2io.h:14 */
 
@@ -157,6 +158,16 @@ struct slicer_handle
     size_t slice = 0;    // particles per slice
     size_t capacity = 0; // records the buffers hold
   } bin;
+  // Part. Degradation (deposit_degrade.cuh): per-particle accepted counts and ranks of the resident batch
+  struct
+  {
+    unsigned char *cnt = nullptr, *keep = nullptr;
+    unsigned *rank = nullptr, *block_sums = nullptr;
+    size_t stride = 0, nblocks = 0, keep_cap = 0;
+    int nplanes = 0;
+    bool valid = false;
+    unsigned long long plane_total[SLICER_MAX_PLANES];
+  } deg;
 };
 
 static int set_device(slicer_handle *h)
@@ -319,6 +330,10 @@ extern "C" void slicer_destroy(slicer_handle *h)
   if (h->comm && g_nccl.CommDestroy)
     g_nccl.CommDestroy(h->comm);
   pipelined_destroy(&h->pipe);
+  cudaFree(h->deg.cnt);
+  cudaFree(h->deg.keep);
+  cudaFree(h->deg.rank);
+  cudaFree(h->deg.block_sums);
   cudaFree(h->bin.rec_u);
   cudaFree(h->bin.rec_s);
   cudaFree(h->bin.key_u);
@@ -389,6 +404,7 @@ extern "C" int slicer_next_batch(slicer_handle *h)
   h->segs.clear();
   h->pos_used = 0;
   h->mass_used = 0;
+  h->deg.valid = false;
   return 0;
 }
 
@@ -679,6 +695,7 @@ static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int npl
       L.acc = h->d_acc + (size_t)i * h->ntypes_alloc * h->npix2max;
       L.counts = h->d_counts + (size_t)i * SLICER_NTYPES * 2;
       L.type_stride = h->cfg.per_type_maps ? h->npix2max : 0;
+      L.slot = i;
       h->plane_npix[i] = d.npix;
       {
         // fraction of a uniform snapshot this plane accepts: slab thickness x (field width / box)^2 at mid-distance
@@ -923,6 +940,195 @@ extern "C" int slicer_deposit(slicer_handle *h, const slicer_plane_desc *planes,
 extern "C" int slicer_deposit_accumulate(slicer_handle *h, const slicer_plane_desc *planes, int nplanes)
 {
   return run_pass(h, planes, nplanes, true);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Part. Degradation
+// ------------------------------------------------------------------------------------------------------------
+static int degrade_prepare(slicer_handle *h, const slicer_plane_desc *planes, int nplanes, PassParams *P, size_t *total)
+{
+  if (!h || !planes)
+    return fail("null argument");
+  if (set_device(h))
+    return 1;
+  if (build_pass(h, planes, nplanes, P))
+    return 1;
+  for (int q = 0; q < nplanes; q++)
+    if ((2 * planes[q].nrepperp + 1) * (2 * planes[q].nrepperp + 1) > 255)
+      return fail("Part. Degradation supports nrepperp <= 7");
+  if (h->copy_pending)
+  {
+    CU(cudaEventRecord(h->ev_copy, h->copy));
+    CU(cudaStreamWaitEvent(h->compute, h->ev_copy, 0));
+    h->copy_pending = false;
+  }
+  size_t n = 0;
+  for (size_t i = 0; i < h->segs.size(); i++)
+    n += h->segs[i].n;
+  *total = n;
+  return 0;
+}
+
+extern "C" int slicer_count_accepted(slicer_handle *h, const slicer_plane_desc *planes, int nplanes, long long *counts)
+{
+  PassParams P;
+  size_t total = 0;
+  if (degrade_prepare(h, planes, nplanes, &P, &total))
+    return 1;
+  if (!counts)
+    return fail("slicer_count_accepted: null output");
+  for (int i = 0; i < nplanes * SLICER_NTYPES; i++)
+    counts[i] = 0;
+  h->deg.valid = false;
+  if (total == 0)
+  {
+    for (int q = 0; q < nplanes; q++)
+      h->deg.plane_total[q] = 0;
+    h->deg.nplanes = nplanes;
+    h->deg.stride = 0;
+    h->deg.valid = true;
+    return 0;
+  }
+  if (h->deg.stride < total || h->deg.nplanes < nplanes)
+  {
+    CU(cudaStreamSynchronize(h->compute));
+    cudaFree(h->deg.cnt);
+    cudaFree(h->deg.rank);
+    cudaFree(h->deg.block_sums);
+    h->deg.cnt = nullptr;
+    h->deg.rank = nullptr;
+    h->deg.block_sums = nullptr;
+    const size_t stride = total + total / 8 + 1024;
+    const size_t nblocks = (stride + 1 + degrade::SCAN_BLOCK * degrade::SCAN_PER - 1) / (degrade::SCAN_BLOCK * degrade::SCAN_PER);
+    const int np = nplanes > h->deg.nplanes ? nplanes : h->deg.nplanes;
+    if (dev_alloc(h, &h->deg.cnt, (size_t)np * stride) || dev_alloc(h, &h->deg.rank, (size_t)np * (stride + 1)) ||
+        dev_alloc(h, &h->deg.block_sums, (size_t)np * nblocks))
+      return 1;
+    h->deg.stride = stride;
+    h->deg.nblocks = nblocks;
+    h->deg.nplanes = np;
+  }
+  const size_t stride = h->deg.stride;
+  CU(cudaMemsetAsync(h->deg.cnt, 0, (size_t)nplanes * stride, h->compute));
+  degrade::Dev G;
+  memset(&G, 0, sizeof(G));
+  G.cnt = h->deg.cnt;
+  G.rank = h->deg.rank;
+  G.stride = stride;
+  std::vector<size_t> seg_start;
+  size_t base = 0;
+  for (size_t si = 0; si < h->segs.size(); si++)
+  {
+    SegmentDev D;
+    fill_segment(h, h->segs[si], &D);
+    seg_start.push_back(base);
+    if (D.n)
+    {
+      G.seg_base = base;
+      const size_t want = (D.n + 255) / 256, cap = (size_t)h->sm_count * 16;
+      const int blocks = (int)(want < cap ? want : cap);
+      if (h->cfg.mas == SLICER_MAS_NGP)
+        degrade::degrade_kernel<SLICER_MAS_NGP, degrade::MARK><<<blocks, 256, 0, h->compute>>>(P, D, G);
+      else
+        degrade::degrade_kernel<SLICER_MAS_TSC, degrade::MARK><<<blocks, 256, 0, h->compute>>>(P, D, G);
+      CU(cudaGetLastError());
+      h->stats.launches++;
+    }
+    base += D.n;
+  }
+  seg_start.push_back(base);
+  const size_t nb = (total + 1 + degrade::SCAN_BLOCK * degrade::SCAN_PER - 1) / (degrade::SCAN_BLOCK * degrade::SCAN_PER);
+  const dim3 grid((unsigned)nb, (unsigned)nplanes);
+  degrade::scan_block_sums<<<grid, degrade::SCAN_BLOCK, 0, h->compute>>>(h->deg.cnt, stride, total, h->deg.block_sums, h->deg.nblocks);
+  degrade::scan_of_block_sums<<<dim3(1, nplanes), 1024, 0, h->compute>>>(h->deg.block_sums, h->deg.nblocks);
+  degrade::scan_finish<<<grid, degrade::SCAN_BLOCK, 0, h->compute>>>(h->deg.cnt, stride, total, h->deg.block_sums, h->deg.nblocks, h->deg.rank);
+  CU(cudaGetLastError());
+  h->stats.launches += 3;
+  // accepted pairs per (plane, segment) = differences of the ranks at the segment boundaries
+  std::vector<unsigned> edge((size_t)nplanes * seg_start.size());
+  for (int q = 0; q < nplanes; q++)
+    for (size_t k = 0; k < seg_start.size(); k++)
+      CU(cudaMemcpyAsync(&edge[q * seg_start.size() + k], h->deg.rank + (size_t)q * (stride + 1) + seg_start[k], sizeof(unsigned),
+                         cudaMemcpyDeviceToHost, h->compute));
+  CU(cudaStreamSynchronize(h->compute));
+  for (int q = 0; q < nplanes; q++)
+  {
+    for (size_t k = 0; k + 1 < seg_start.size(); k++)
+      counts[q * SLICER_NTYPES + h->segs[k].type] += (long long)(edge[q * seg_start.size() + k + 1] - edge[q * seg_start.size() + k]);
+    h->deg.plane_total[q] = edge[q * seg_start.size() + seg_start.size() - 1];
+  }
+  h->deg.valid = true;
+  return 0;
+}
+
+extern "C" int slicer_deposit_degraded(slicer_handle *h, const slicer_plane_desc *planes, int nplanes, int snopt,
+                                       const unsigned char *const *keep, int accumulate)
+{
+  PassParams P;
+  size_t total = 0;
+  if (degrade_prepare(h, planes, nplanes, &P, &total))
+    return 1;
+  if (snopt < 1 || snopt > 30)
+    return fail("slicer_deposit_degraded: snopt %d outside 1..30", snopt);
+  if (!h->deg.valid || h->deg.nplanes < nplanes)
+    return fail("slicer_deposit_degraded: call slicer_count_accepted for this batch and these planes first");
+  if (!accumulate)
+  {
+    CU(cudaMemsetAsync(h->d_acc, 0, (size_t)nplanes * h->ntypes_alloc * h->npix2max * sizeof(unsigned long long), h->compute));
+    CU(cudaMemsetAsync(h->d_counts, 0, (size_t)nplanes * SLICER_NTYPES * 2 * sizeof(unsigned long long), h->compute));
+  }
+  if (total == 0)
+    return 0;
+  degrade::Dev G;
+  memset(&G, 0, sizeof(G));
+  size_t need = 0;
+  for (int q = 0; q < nplanes; q++)
+  {
+    G.keep_off[q] = need;
+    need += h->deg.plane_total[q];
+    if (h->deg.plane_total[q] && (!keep || !keep[q]))
+      return fail("slicer_deposit_degraded: keep table of plane %d is missing", q);
+  }
+  if (need > h->deg.keep_cap)
+  {
+    CU(cudaStreamSynchronize(h->compute));
+    cudaFree(h->deg.keep);
+    h->deg.keep = nullptr;
+    if (dev_alloc(h, &h->deg.keep, need + need / 4 + 4096))
+      return 1;
+    h->deg.keep_cap = need + need / 4 + 4096;
+  }
+  for (int q = 0; q < nplanes; q++)
+    if (h->deg.plane_total[q])
+      CU(cudaMemcpyAsync(h->deg.keep + G.keep_off[q], keep[q], h->deg.plane_total[q], cudaMemcpyHostToDevice, h->compute));
+  G.cnt = h->deg.cnt;
+  G.rank = h->deg.rank;
+  G.keep = h->deg.keep;
+  G.stride = h->deg.stride;
+  G.snopt = snopt;
+  size_t base = 0;
+  for (size_t si = 0; si < h->segs.size(); si++)
+  {
+    SegmentDev D;
+    fill_segment(h, h->segs[si], &D);
+    if (D.n)
+    {
+      G.seg_base = base;
+      const size_t want = (D.n + 255) / 256, cap = (size_t)h->sm_count * 16;
+      const int blocks = (int)(want < cap ? want : cap);
+      if (h->cfg.mas == SLICER_MAS_NGP)
+        degrade::degrade_kernel<SLICER_MAS_NGP, degrade::DEPOSIT><<<blocks, 256, 0, h->compute>>>(P, D, G);
+      else
+        degrade::degrade_kernel<SLICER_MAS_TSC, degrade::DEPOSIT><<<blocks, 256, 0, h->compute>>>(P, D, G);
+      CU(cudaGetLastError());
+      h->stats.launches++;
+      h->stats.particles_streamed += D.n;
+    }
+    base += D.n;
+  }
+  CU(cudaEventRecord(h->ev_buf_done[h->cur_buf], h->compute));
+  CU(cudaStreamSynchronize(h->compute)); // the caller's keep tables may be freed on return
+  return 0;
 }
 
 extern "C" int slicer_synchronize(slicer_handle *h)

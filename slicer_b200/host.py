@@ -25,6 +25,7 @@ def lib():
         L.shost_plan.argtypes = ([C.c_double] * 4 + [C.c_int, _f64p, _f64p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int),
                                                      C.POINTER(C.c_double)] + [_f64p] * 4 + [_i32p] * 3 + [C.POINTER(C.c_int)])
         L.shost_randomize_box.argtypes = [C.c_int] * 4 + [_i32p, C.c_int, _f64p, _f64p, _f64p, _i32p, _i32p, _i32p, _i32p]
+        L.shost_glibc_rand.argtypes = [C.c_uint, C.c_int, _i32p]
         L.shost_read_input.argtypes = [C.c_char_p, _i32p, _f64p, C.c_char_p]
         L.shost_read_subfile.argtypes = [C.c_char_p, C.c_int, _i32p, _f64p, _f64p, C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_longlong]
         L.shost_write_fits.argtypes = [C.c_char_p, _f32p, C.c_int, C.c_int, C.POINTER(C.c_char_p), _f64p, C.c_int, C.POINTER(C.c_char_p),
@@ -62,6 +63,12 @@ def randomize_box(seedcenter, seedface, seedsign, randomize, fixed_vertex=False)
     face, sx, sy, sz = (np.zeros(n, np.int32) for _ in range(4))
     lib().shost_randomize_box(seedcenter, seedface, seedsign, n, randomize, int(fixed_vertex), x0, y0, z0, face, sx, sy, sz)
     return dict(x0=x0, y0=y0, z0=z0, face=face, sgnX=sx, sgnY=sy, sgnZ=sz)
+
+
+def glibc_rand(seed, n):
+    out = np.zeros(n, np.int32)
+    lib().shost_glibc_rand(C.c_uint(seed & 0xFFFFFFFF), n, out)
+    return out
 
 
 def read_input(path):

@@ -120,15 +120,145 @@ static int fail_capi(const char *what)
   return 1;
 }
 
+// Stage every particle type of a sub-file that is already in `buf` (types in order: the order mapParticles walks them).
+static int stage_subfile(slicer_handle *h, const SubFile &buf, bool hydro)
+{
+  size_t off = 0;
+  for (int t = 0; t < 6; t++)
+  {
+    const size_t nt = (size_t)buf.header.npart[t];
+    if (nt)
+    {
+      const bool pm = hydro && buf.header.massarr[t] == 0;
+      if (slicer_stage_particles(h, t, buf.pos + 3 * off, SLICER_LAYOUT_AOS, pm ? buf.mass + off : nullptr, nt))
+        return fail_capi("slicer_stage_particles");
+    }
+    off += nt;
+  }
+  return 0;
+}
+
+// `Part. Degradation` (snopt > 0, densitymaps.cpp:387-397).  The reference consumes one libc rand() per accepted
+// (particle, replica) pair, plane after plane, sub-file after sub-file, type after type, particle after particle —
+// one serial stream that continues from randomizeBox's last srand().  Sweep 1 counts the accepted pairs of every
+// (plane, sub-file, type); the draws are then made here, in that order, with the same libc generator; sweep 2 applies
+// them on the device by rank (slicer_count_accepted / slicer_deposit_degraded).
+static int createDensityMapsDegraded(Engine *e, InputParams &p, Lens &lens, Random &random, const std::vector<PlaneJob> &jobs, unsigned ffmin,
+                                     unsigned ffmax, const std::string &File, double fovradiants, std::vector<std::valarray<float>> &mapxytot,
+                                     std::vector<std::valarray<float>> &mapxytoti, std::vector<long long> &ntotxyi, int myid)
+{
+  const int nj = (int)jobs.size();
+  if (nj > SLICER_MAX_PLANES)
+  {
+    std::cerr << "Part. Degradation: more than " << SLICER_MAX_PLANES << " planes share one snapshot; not supported" << std::endl;
+    return 1;
+  }
+  mapxytot.assign(nj, std::valarray<float>());
+  mapxytoti.assign((size_t)nj * 6, std::valarray<float>());
+  ntotxyi.assign((size_t)nj * 6, 0);
+  const int ngpu = (int)e->h.size();
+  const unsigned nff = ffmax - ffmin;
+  std::vector<slicer_plane_desc> descs;
+  for (int j = 0; j < nj; j++)
+    descs.push_back(make_desc(lens, random, jobs[j].isnap, jobs[j].rcase, fovradiants, jobs[j].npix));
+  // ---- sweep 1: accepted pairs per (plane, sub-file, type)
+  std::vector<long long> cnt((size_t)nff * nj * 6, 0);
+  for (unsigned ff = ffmin; ff < ffmax; ff++)
+  {
+    const int g = (int)((ff - ffmin) % ngpu);
+    SubFile &buf = e->bufs[2 * g];
+    if (slicer_synchronize(e->h[g]) || readSubFile(File + "." + std::to_string(ff), p.hydro, buf, true))
+      return 1;
+    if (buf.ntotal > e->capacity)
+    {
+      std::cerr << "sub-file " << ff << " holds " << buf.ntotal << " particles, more than the engine's capacity " << e->capacity << std::endl;
+      return 1;
+    }
+    if (slicer_begin_snapshot(e->h[g], buf.header.boxsize, buf.header.massarr, p.hydro) || stage_subfile(e->h[g], buf, p.hydro))
+      return fail_capi("staging");
+    if (slicer_count_accepted(e->h[g], descs.data(), nj, &cnt[(size_t)(ff - ffmin) * nj * 6]))
+      return fail_capi("slicer_count_accepted");
+  }
+  // ---- the draws, in the reference's order: plane-major, then sub-file, then type/particle/replica
+  const double thr = 1. / pow(2, p.snopt);
+  std::vector<std::vector<unsigned char>> keep((size_t)nj * nff);
+  for (int j = 0; j < nj; j++)
+    for (unsigned f = 0; f < nff; f++)
+    {
+      long long n = 0;
+      for (int t = 0; t < 6; t++)
+        n += cnt[((size_t)f * nj + j) * 6 + t];
+      std::vector<unsigned char> &k = keep[(size_t)j * nff + f];
+      k.resize((size_t)n);
+      for (long long i = 0; i < n; i++)
+        k[i] = (sharedRand().next() / float(RAND_MAX) < thr) ? 1 : 0; // densitymaps.cpp:393
+    }
+  // ---- sweep 2: deposit with the draws applied by rank
+  std::fill(e->used.begin(), e->used.end(), 0);
+  Header first_header;
+  bool have_header = false;
+  for (unsigned ff = ffmin; ff < ffmax; ff++)
+  {
+    const int g = (int)((ff - ffmin) % ngpu);
+    SubFile &buf = e->bufs[2 * g];
+    if (slicer_synchronize(e->h[g]) || readSubFile(File + "." + std::to_string(ff), p.hydro, buf, true))
+      return 1;
+    if (!have_header)
+    {
+      first_header = buf.header;
+      have_header = true;
+    }
+    if (myid == 0)
+      std::cout << " sub-file " << ff << ": " << buf.ntotal << " particles -> GPU " << e->devices[g] << " (degradation 2^-" << p.snopt << ")" << std::endl;
+    if (slicer_begin_snapshot(e->h[g], buf.header.boxsize, buf.header.massarr, p.hydro) || stage_subfile(e->h[g], buf, p.hydro))
+      return fail_capi("staging");
+    std::vector<long long> again((size_t)nj * 6);
+    if (slicer_count_accepted(e->h[g], descs.data(), nj, again.data()))
+      return fail_capi("slicer_count_accepted");
+    std::vector<const unsigned char *> kp(nj);
+    for (int j = 0; j < nj; j++)
+      kp[j] = keep[(size_t)j * nff + (ff - ffmin)].data();
+    if (slicer_deposit_degraded(e->h[g], descs.data(), nj, p.snopt, kp.data(), e->used[g] > 0))
+      return fail_capi("slicer_deposit_degraded");
+    e->used[g]++;
+  }
+  for (int g = 0; g < ngpu; g++)
+    if (e->used[g] == 0)
+    {
+      const double zero[6] = {0, 0, 0, 0, 0, 0};
+      if (slicer_begin_snapshot(e->h[g], have_header ? first_header.boxsize : 1.0, have_header ? first_header.massarr : zero, p.hydro) ||
+          slicer_deposit(e->h[g], descs.data(), nj))
+        return fail_capi("slicer_deposit");
+    }
+  if (ngpu > 1 && slicer_reduce_all(e->h.data(), ngpu, nj, 0))
+    return fail_capi("slicer_reduce_all");
+  for (int j = 0; j < nj; j++)
+  {
+    const int npix = jobs[j].npix;
+    long long counts[6];
+    mapxytot[j].resize((size_t)npix * npix);
+    if (slicer_fetch(e->h[0], j, -1, &mapxytot[j][0], counts, nullptr))
+      return fail_capi("slicer_fetch");
+    for (int t = 0; t < 6; t++)
+    {
+      ntotxyi[(size_t)j * 6 + t] = counts[t];
+      if (e->per_type)
+      {
+        mapxytoti[(size_t)j * 6 + t].resize((size_t)npix * npix);
+        if (slicer_fetch(e->h[0], j, t, &mapxytoti[(size_t)j * 6 + t][0], nullptr, nullptr))
+          return fail_capi("slicer_fetch");
+      }
+    }
+  }
+  return 0;
+}
+
 int createDensityMapsMulti(Engine *e, InputParams &p, Lens &lens, Random &random, const std::vector<PlaneJob> &jobs, unsigned ffmin,
                            unsigned ffmax, const std::string &File, double fovradiants, std::vector<std::valarray<float>> &mapxytot,
                            std::vector<std::valarray<float>> &mapxytoti, std::vector<long long> &ntotxyi, int myid)
 {
   if (p.snopt > 0)
-  {
-    std::cerr << "Part. Degradation (snopt > 0) is not implemented on the GPU path yet" << std::endl;
-    return 1;
-  }
+    return createDensityMapsDegraded(e, p, lens, random, jobs, ffmin, ffmax, File, fovradiants, mapxytot, mapxytoti, ntotxyi, myid);
   const int njobs = (int)jobs.size();
   mapxytot.assign(njobs, std::valarray<float>());
   mapxytoti.assign((size_t)njobs * 6, std::valarray<float>());

@@ -84,6 +84,16 @@ extern "C"
     return 0;
   }
 
+  // n outputs of GlibcRand after seed(s) (tests compare with libc srand/rand)
+  int shost_glibc_rand(unsigned int s, int n, int *out)
+  {
+    GlibcRand g;
+    g.seed(s);
+    for (int i = 0; i < n; i++)
+      out[i] = g.next();
+    return 0;
+  }
+
   int shost_read_input(const char *file, int *ints /* npix, seedcenter, seedface, seedsign, partinplanes, snopt, physical, rgrid */,
                        double *dbl /* zs, fov, w */, char *strings /* 6 x 512: list, pathsnap, simulation, directory, suffix, snpix */)
   {

@@ -351,7 +351,41 @@ int buildPlanes(InputParams &p, Lens &lens, std::vector<double> &snapred, std::v
   return 0;
 }
 
-// densitymaps.cpp:166-248 — libc srand/rand, like the reference binary (glibc TYPE_3 generator state is global)
+void GlibcRand::seed(unsigned int s)
+{
+  if (s == 0)
+    s = 1;
+  r_[0] = (int32_t)s;
+  for (int i = 1; i < 31; i++)
+  {
+    const long hi = r_[i - 1] / 127773, lo = r_[i - 1] % 127773;
+    long word = 16807 * lo - 2836 * hi;
+    if (word < 0)
+      word += 2147483647;
+    r_[i] = (int32_t)word;
+  }
+  f_ = 3;
+  b_ = 0;
+  for (int i = 0; i < 310; i++)
+    next();
+}
+
+int GlibcRand::next()
+{
+  const uint32_t v = (uint32_t)r_[f_] + (uint32_t)r_[b_];
+  r_[f_] = (int32_t)v;
+  f_ = f_ + 1 == 31 ? 0 : f_ + 1;
+  b_ = b_ + 1 == 31 ? 0 : b_ + 1;
+  return (int)(v >> 1);
+}
+
+GlibcRand &sharedRand()
+{
+  static GlibcRand g;
+  return g;
+}
+
+// densitymaps.cpp:166-248 — the reference uses libc srand/rand; GlibcRand is the same generator with private state
 void randomizeBox(Random &random, const Lens &lens, const InputParams &p, int numOfLensPerSnap, int myid, bool fixedVertex)
 {
   const size_t nrandom = lens.replication.back();
@@ -366,12 +400,13 @@ void randomizeBox(Random &random, const Lens &lens, const InputParams &p, int nu
   {
     if (lens.randomize[i])
     {
-      srand(p.seedcenter + i / numOfLensPerSnap * 13);
+      GlibcRand &R = sharedRand();
+      R.seed(p.seedcenter + i / numOfLensPerSnap * 13);
       if (!fixedVertex)
       {
-        random.x0[i] = rand() / float(RAND_MAX);
-        random.y0[i] = rand() / float(RAND_MAX);
-        random.z0[i] = rand() / float(RAND_MAX);
+        random.x0[i] = R.next() / float(RAND_MAX);
+        random.y0[i] = R.next() / float(RAND_MAX);
+        random.z0[i] = R.next() / float(RAND_MAX);
       }
       else
       { // -DFixedPLCVertex, densitymaps.cpp:191-195
@@ -380,16 +415,16 @@ void randomizeBox(Random &random, const Lens &lens, const InputParams &p, int nu
         random.z0[i] = 0.5;
       }
       random.face[i] = 7;
-      srand(p.seedface + i / numOfLensPerSnap * 5);
+      R.seed(p.seedface + i / numOfLensPerSnap * 5);
       while (random.face[i] > 6 || random.face[i] < 1)
-        random.face[i] = int(1 + rand() / float(RAND_MAX) * 5. + 0.5);
-      srand(p.seedsign + i / numOfLensPerSnap * 8);
+        random.face[i] = int(1 + R.next() / float(RAND_MAX) * 5. + 0.5);
+      R.seed(p.seedsign + i / numOfLensPerSnap * 8);
       int *sg[3] = {&random.sgnX[i], &random.sgnY[i], &random.sgnZ[i]};
       for (int k = 0; k < 3; k++)
       {
         *sg[k] = 2;
         while (*sg[k] > 1 || *sg[k] < 0)
-          *sg[k] = int(rand() / float(RAND_MAX) + 0.5);
+          *sg[k] = int(R.next() / float(RAND_MAX) + 0.5);
         if (*sg[k] == 0)
           *sg[k] = -1;
       }

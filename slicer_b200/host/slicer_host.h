@@ -101,6 +101,21 @@ struct CosmoTable // slicer-v2.cpp:79-96
   void build(double om0, double oml, double w, double zs);
 };
 
+// glibc's rand()/srand() (random_r.c, TYPE_3: additive feedback x^31 + x^3 + 1, seeded by the 16807 Lehmer LCG, 310
+// outputs discarded), restated so that the draws of randomizeBox and of `Part. Degradation` do not depend on — and are
+// not disturbed by — the process-wide libc state (CUDA, NCCL or user code may call rand()).  Checked against libc in
+// tests/test_host_layer.py.
+class GlibcRand
+{
+public:
+  void seed(unsigned int s);
+  int next(); // 0 .. RAND_MAX (2147483647)
+private:
+  int32_t r_[34];
+  int f_ = 3, b_ = 0;
+};
+GlibcRand &sharedRand(); // the stream the reference's global rand() state corresponds to
+
 struct SliceError
 {
   std::string what;

@@ -39,7 +39,7 @@ gadget
 ##### 12. PLC Suffix ###########
 0
 ##### 13. Part. Degradation ####
-0
+{snopt}
 ##### 14. DE-EOS w #############
 -1.0
 """
@@ -82,14 +82,14 @@ def make_dataset(tmp_path, ng=48, nsnap=4, numfiles=2, hydro=False):
     return str(snapdir) + "/", str(lst)
 
 
-def run_both(tmp_path, npix, zs, fov, ref_exe, extra=(), pip=0, hydro=False, numfiles=2):
+def run_both(tmp_path, npix, zs, fov, ref_exe, extra=(), pip=0, hydro=False, numfiles=2, snopt=0):
     snapdir, lst = make_dataset(tmp_path, hydro=hydro, numfiles=numfiles)
     outs = {}
     for tag, exe in (("ref", [ref_exe]), ("gpu", [host.EXE_PATH, "--quiet", *extra])):
         out = tmp_path / f"out_{tag}"
         out.mkdir()
         ini = tmp_path / f"InputParams_{tag}.ini"
-        ini.write_text(INI.format(npix=npix, zs=zs, fov=fov, list=lst, snapdir=snapdir, outdir=str(out) + "/test_", pip=pip))
+        ini.write_text(INI.format(npix=npix, zs=zs, fov=fov, list=lst, snapdir=snapdir, outdir=str(out) + "/test_", pip=pip, snopt=snopt))
         r = subprocess.run(exe + [str(ini)], cwd=tmp_path, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stderr[-2000:] + r.stdout[-2000:]
         outs[tag] = out
@@ -133,8 +133,8 @@ def test_driver_hydro_per_type_files(tmp_path):
     out_ref.mkdir()
     out_gpu.mkdir()
     ini_ref, ini_gpu = tmp_path / "ref.ini", tmp_path / "gpu.ini"
-    ini_ref.write_text(INI.format(npix=128, zs=0.2, fov=6.0, list=lst, snapdir=snapdir, outdir=str(out_ref) + "/test_", pip=0))
-    ini_gpu.write_text(INI.format(npix=128, zs=0.2, fov=6.0, list=lst, snapdir=snapdir, outdir=str(out_gpu) + "/test_", pip=1))
+    ini_ref.write_text(INI.format(npix=128, zs=0.2, fov=6.0, list=lst, snapdir=snapdir, outdir=str(out_ref) + "/test_", pip=0, snopt=0))
+    ini_gpu.write_text(INI.format(npix=128, zs=0.2, fov=6.0, list=lst, snapdir=snapdir, outdir=str(out_gpu) + "/test_", pip=1, snopt=0))
     assert subprocess.run([REF_EXE, str(ini_ref)], cwd=tmp_path, capture_output=True, timeout=900).returncode == 0
     r = subprocess.run([host.EXE_PATH, "--quiet", str(ini_gpu)], cwd=tmp_path, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -160,7 +160,7 @@ def test_driver_resume_skips_existing_planes(tmp_path):
     out = tmp_path / "out"
     out.mkdir()
     ini = tmp_path / "p.ini"
-    ini.write_text(INI.format(npix=32, zs=0.1, fov=5.0, list=lst, snapdir=snapdir, outdir=str(out) + "/t_", pip=0))
+    ini.write_text(INI.format(npix=32, zs=0.1, fov=5.0, list=lst, snapdir=snapdir, outdir=str(out) + "/t_", pip=0, snopt=0))
     assert subprocess.run([host.EXE_PATH, "--quiet", str(ini)], cwd=tmp_path, capture_output=True, timeout=600).returncode == 0
     files = sorted(f for f in os.listdir(out) if f.endswith(".fits"))
     assert len(files) >= 8
@@ -184,7 +184,7 @@ def test_driver_two_gpus_matches_one_gpu(tmp_path):
         out = tmp_path / tag
         out.mkdir()
         ini = tmp_path / f"{tag}.ini"
-        ini.write_text(INI.format(npix=64, zs=0.1, fov=6.0, list=lst, snapdir=snapdir, outdir=str(out) + "/t_", pip=0))
+        ini.write_text(INI.format(npix=64, zs=0.1, fov=6.0, list=lst, snapdir=snapdir, outdir=str(out) + "/t_", pip=0, snopt=0))
         r = subprocess.run([host.EXE_PATH, "--quiet", "--gpus", gpus, str(ini)], cwd=tmp_path, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stderr[-2000:]
         outs[tag] = out
@@ -192,3 +192,21 @@ def test_driver_two_gpus_matches_one_gpu(tmp_path):
     assert len(files) >= 8
     for f in files:
         assert open(outs["g1"] / f, "rb").read() == open(outs["g2"] / f, "rb").read(), f
+
+
+@pytest.mark.parametrize("snopt,hydro", [(1, False), (2, True)])
+def test_driver_part_degradation_matches_reference(tmp_path, snopt, hydro):
+    """Part. Degradation = 1, 2: the reference's serial rand() stream (continuing from randomizeBox, plane after plane,
+    sub-file after sub-file) is reproduced exactly, so every plane matches the reference executable's."""
+    if not os.path.exists(REF_EXE):
+        pytest.skip("oracle/_ref/SLICER_ref not built")
+    outs = run_both(tmp_path, 64, 0.2, 6.0, REF_EXE, snopt=snopt, hydro=hydro, numfiles=3)
+    ref_files = sorted(f for f in os.listdir(outs["ref"]) if f.endswith(".fits"))
+    assert ref_files == sorted(f for f in os.listdir(outs["gpu"]) if f.endswith(".fits")) and len(ref_files) >= 16
+    total = 0.0
+    for f in ref_files:
+        _, rimg = read_shim_fits(outs["ref"] / f)
+        _, gimg = host.read_fits(str(outs["gpu"] / f))
+        np.testing.assert_allclose(gimg, rimg, rtol=1e-6, atol=1e-9)
+        total += float(rimg.sum(dtype=np.float64))
+    assert total > 100.0

@@ -279,3 +279,44 @@ def test_binned_deposit_large_map(oracle):
             _, counts, ingrid = s.fetch(k, -1, npix, want_map=False)
             assert counts.tolist() == res["counts"].tolist() and counts[1] > 20000
             assert np.array_equal(s.fetch_fixed(k, -1, npix).reshape(-1), res["fixed"][1])
+
+
+@pytest.mark.parametrize("snopt,nrep", [(1, 0), (2, 0), (1, 1)])
+def test_part_degradation_matches_oracle(oracle, snopt, nrep):
+    """snopt > 0 (densitymaps.cpp:387-397): one libc rand() per accepted pair in the reference's order decides whether the
+    pair weighs 2^snopt m or 0.  The draws are made on the host and applied on the device by rank: int64 maps == oracle."""
+    from oracle.oracle_bindings import libc_rand, libc_srand
+
+    box = 90000.0
+    rng = np.random.default_rng(8)
+    pos = {1: synth.uniform_positions(40000, box, 61), 4: synth.uniform_positions(9000, box, 62)}
+    mass4 = (rng.random(9000) * 2).astype(np.float32)
+    mass4[::9] = 3e3
+    plane = dict(boxsize=box, sgn=[1, -1, -1], face=3, centre=[0.2, 0.4, 0.6], rcase=1.0, ld=90.0 + 22.5, ld2=90.0 + 45.0, nrepperp=nrep,
+                 fovradiants=0.9 if nrep == 0 else 1.6)
+    npix = 64
+    d = capi.plane_desc(plane["sgn"], plane["face"], plane["centre"], plane["rcase"], plane["ld"], plane["ld2"], plane["fovradiants"], npix, nrep)
+    seed = 4242 + snopt
+    with capi.Slicer(npix_max=npix, max_planes=1, mas=capi.MAS_TSC, particle_capacity=60000, mass_capacity=60000, per_type_maps=True) as s:
+        s.begin_snapshot(box, [0, 0.75, 0, 0, 0, 0], True)
+        s.stage(1, pos[1])
+        s.stage(4, pos[4], mass4)
+        counts = s.count_accepted([d])
+        total = int(counts.sum())
+        libc_srand(seed)
+        keep = np.array([1 if np.float32(libc_rand()) / np.float32(2147483647) < 1.0 / 2 ** snopt else 0 for _ in range(total)], np.uint8)
+        s.deposit_degraded([d], snopt, [keep])
+        fb = s.frac_bits
+        got = {t: s.fetch_fixed(0, t, npix).reshape(-1) for t in (1, 4)}
+        _, c2, _ = s.fetch(0, -1, npix, want_map=False)
+    assert c2.tolist() == counts[0].tolist()
+    # oracle: same libc stream, types in order (mapParticles walks type 1 then type 4)
+    libc_srand(seed)
+    for t, kw in ((1, dict(const_mass=0.75)), (4, dict(per_particle=mass4))):
+        x, y, z = oracle.transform(pos[t], box, plane["sgn"], plane["face"], plane["centre"], plane["rcase"])
+        xs, ys, ms = oracle.select_project(x, y, z, plane["ld"], plane["ld2"], box, nrep, plane["fovradiants"], npix, snopt=snopt,
+                                           cap=len(x) * (2 * nrep + 1) ** 2, **kw)
+        assert len(xs) == counts[0][t] and len(xs) > 500
+        assert 0.2 < np.count_nonzero(ms) / max(1, np.count_nonzero(ms >= 0) ) < 0.8 or snopt == 2
+        want = oracle.gridist_w_fixed(xs, ys, ms, npix, fb)
+        assert np.array_equal(got[t], want), f"type {t}"

@@ -114,3 +114,13 @@ def test_fits_writer_layout(tmp_path):
     assert hdr["DlLOW"] == 228.57142857142858 and hdr["nparttype1"] == 1224 and hdr["PHYSICALSIZE"] == 2.0
     assert np.array_equal(back, img)  # element [gy, gx] <-> map[gx + npix*gy], big-endian on disk
     assert host.write_fits(f, img, [], []) == 1  # an existing file is not overwritten (FITS::CantCreate)
+
+
+def test_glibc_rand_restatement_matches_libc():
+    """slicer::GlibcRand (private state) == libc srand/rand, which the reference uses (densitymaps.cpp:187-223, :393)."""
+    from oracle.oracle_bindings import libc_rand, libc_srand
+
+    for seed in (1, 0, -229, -230, -231, 12345, 2 ** 31 - 1, 2 ** 32 - 5):
+        libc_srand(seed)
+        want = [libc_rand() for _ in range(3000)]
+        assert host.glibc_rand(seed, 3000).tolist() == want
