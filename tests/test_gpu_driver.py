@@ -210,3 +210,51 @@ def test_driver_part_degradation_matches_reference(tmp_path, snopt, hydro):
         np.testing.assert_allclose(gimg, rimg, rtol=1e-6, atol=1e-9)
         total += float(rimg.sum(dtype=np.float64))
     assert total > 100.0
+
+
+def _compare_dirs(out_ref, out_gpu, npix=None, min_files=8):
+    ref_files = sorted(f for f in os.listdir(out_ref) if f.endswith(".fits"))
+    assert ref_files == sorted(f for f in os.listdir(out_gpu) if f.endswith(".fits")) and len(ref_files) >= min_files
+    total = 0.0
+    for f in ref_files:
+        rk, rimg = read_shim_fits(out_ref / f)
+        gk, gimg = host.read_fits(str(out_gpu / f))
+        assert gimg.shape == rimg.shape
+        if npix:
+            assert rimg.shape == (npix, npix)
+        for k in ("REDSHIFT", "DlLOW", "DlUP"):
+            assert gk[k] == rk[k]
+        np.testing.assert_allclose(gimg, rimg, rtol=1e-6, atol=1e-9)
+        total += float(rimg.sum(dtype=np.float64))
+    assert total > 50.0
+    return ref_files
+
+
+def test_driver_perpendicular_replication(tmp_path):
+    """CMake USE_REPLICATION (-DReplicationOnPerpendicularPlane): a field wider than the box is filled with
+    replicas (computeReplications, densitymaps.cpp:275-283; mapParticles' ni, nj loops :377-378)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "SLICER_ref_repl")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/SLICER_ref_repl not built")
+    outs = run_both(tmp_path, 64, 0.2, 25.0, exe, extra=("--replication",))  # 25 deg at 590 Mpc/h = 257 Mpc/h > 128 Mpc/h box
+    _compare_dirs(outs["ref"], outs["gpu"], 64, 16)
+
+
+def test_driver_fixed_plc_vertex(tmp_path):
+    """CMake USE_FIXED_PLC_VERTEX (-DFixedPLCVertex): no random centre shift (densitymaps.cpp:186-196)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "SLICER_ref_fixed")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/SLICER_ref_fixed not built")
+    outs = run_both(tmp_path, 64, 0.2, 6.0, exe, extra=("--fixed-vertex",))
+    _compare_dirs(outs["ref"], outs["gpu"], 64, 16)
+
+
+def test_driver_physical_pixel_mode(tmp_path):
+    """npix < 0: `physical` mode, -npix kpc/h pixels, map side recomputed per plane (data.cpp:64-78, slicer-v2.cpp:142-143)."""
+    if not os.path.exists(REF_EXE):
+        pytest.skip("oracle/_ref/SLICER_ref not built")
+    outs = run_both(tmp_path, -500, 0.2, 6.0, REF_EXE)
+    files = _compare_dirs(outs["ref"], outs["gpu"], None, 16)
+    assert all("_500_kpc_" in f for f in files)
+    sides = {host.read_fits(str(outs["gpu"] / f))[0]["NAXIS1"] for f in files}
+    assert len(sides) > 4  # the map grows with distance
