@@ -309,7 +309,7 @@ def ours(args, rank, world, local_rank):
     achieved = 12.0 * npart / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "one pass = pipe::deposit_pipelined_kernel<TSC,AOS,SINGLE,*> (stream + screen + exact projection) "
-                "[+ binned::bin_* sort + binned::tile_deposit_kernel when > 1 % of the snapshot is inside the field]", "kernel_ms": kernel_ms,
+                "[+ binned::bin_* sort + binned::tile_deposit_kernel when > 3 % of the snapshot is inside the field]", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": 12 * npart, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else
                 "fallback 6650 GB/s"}
     prof = os.path.join(ROOT, "profiles", "r01_traffic.json")

@@ -5,6 +5,7 @@
 // (the reference deals them to MPI ranks, :162-175) and the planes are summed with ncclReduce instead of MPI_Reduce.
 #include "slicer_host.h"
 
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -12,6 +13,10 @@
 
 namespace slicer
 {
+
+// wall-clock phase totals of the last runLightCone (seconds): printed when SLICER_B200_TIMING is set
+static double t_read = 0, t_submit = 0, t_fetch = 0, t_write = 0, t_engine = 0;
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct Engine
 {
@@ -279,8 +284,10 @@ int createDensityMapsMulti(Engine *e, InputParams &p, Lens &lens, Random &random
       SubFile &buf = e->bufs[2 * g + (e->used[g] & 1)];
       if (e->used[g] >= 2 && slicer_wait_staging(e->h[g])) // the copy that last read this host buffer must be done
         return fail_capi("slicer_wait_staging");
+      const double tr0 = now_s();
       if (readSubFile(File + "." + std::to_string(ff), p.hydro, buf, true))
         return 1;
+      t_read += now_s() - tr0;
       const Header &data = buf.header;
       if (!have_header)
       {
@@ -330,6 +337,7 @@ int createDensityMapsMulti(Engine *e, InputParams &p, Lens &lens, Random &random
       }
     if (ngpu > 1 && slicer_reduce_all(e->h.data(), ngpu, nj, 0)) // replaces the 7 MPI_Reduce of slicer-v2.cpp:214-217
       return fail_capi("slicer_reduce_all");
+    const double tf0 = now_s();
     for (int j = 0; j < nj; j++)
     {
       const int npix = jobs[j0 + j].npix;
@@ -348,6 +356,7 @@ int createDensityMapsMulti(Engine *e, InputParams &p, Lens &lens, Random &random
         }
       }
     }
+    t_fetch += now_s() - tf0;
   }
   return 0;
 }
@@ -383,6 +392,8 @@ static std::string plane_label(int pll)
 int runLightCone(const std::string &inifile, const RunOptions &opt)
 {
   const int myid = opt.quiet ? 1 : 0;
+  const double t_begin = now_s();
+  t_read = t_submit = t_fetch = t_write = t_engine = 0;
   InputParams p;
   if (readInput(p, inifile))
     return 1;
@@ -474,7 +485,9 @@ int runLightCone(const std::string &inifile, const RunOptions &opt)
         for (int i = 0; i < 6; i++)
           tot += (size_t)snapdata.npartTotal[i] + ((size_t)(uint32_t)snapdata.nTotalHW[i] << 32);
         const size_t cap = tot / std::max(1, snapdata.numfiles) * 5 / 4 + 65536;
+        const double te0 = now_s();
         e = engineCreate(opt.devices, npix_max, opt.mas, p.partinplanes, cap, opt.deposit_mode);
+        t_engine += now_s() - te0;
         if (!e)
         {
           status = 1;
@@ -494,9 +507,11 @@ int runLightCone(const std::string &inifile, const RunOptions &opt)
         const double zsim = cosmo.getZl.eval((lens.ld2[isnap] + lens.ld[isnap]) / 2.0);
         InputParams pj = p;
         pj.npix = jobs[j].npix;
+        const double tw0 = now_s();
         try
         {
           writeMaps(pj, snapdata, lens, isnap, zsim, plane_label(lens.pll[isnap]), tot[j], p.partinplanes ? &per[j * 6] : nullptr, &cnt[j * 6], 0);
+          t_write += now_s() - tw0;
         }
         catch (const SliceError &err)
         {
@@ -509,6 +524,9 @@ int runLightCone(const std::string &inifile, const RunOptions &opt)
     s0 = s1;
   }
   engineDestroy(e);
+  if (getenv("SLICER_B200_TIMING"))
+    std::cerr << "[timing] total " << now_s() - t_begin << " s: engine/CUDA set-up " << t_engine << ", sub-file reads " << t_read << ", fetch (waits for the GPU) " << t_fetch
+              << ", FITS writes " << t_write << std::endl;
   return status;
 }
 

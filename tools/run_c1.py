@@ -29,12 +29,12 @@ for tag, exe in (("gpu", [host.EXE_PATH, "--quiet"]), ("ref", [os.path.join(ROOT
     out = f"{work}/out_{tag}"
     subprocess.run(["rm", "-rf", out]); os.makedirs(out)
     ini = f"{work}/{tag}.ini"
-    open(ini, "w").write(INI.format(npix=256, zs=0.5, fov=2.0, list=work + "/snapshot_list.txt", snapdir=work + "/snaps/", outdir=out + "/test_", pip=0))
+    open(ini, "w").write(INI.format(npix=256, zs=0.5, fov=2.0, list=work + "/snapshot_list.txt", snapdir=work + "/snaps/", outdir=out + "/test_", pip=0, snopt=0))
     t0 = time.time()
-    r = subprocess.run(exe + [ini], cwd=work, capture_output=True, text=True)
+    r = subprocess.run(exe + [ini], cwd=work, capture_output=True, text=True, env=dict(os.environ, SLICER_B200_TIMING="1"))
     res[tag] = time.time() - t0
     assert r.returncode == 0, r.stderr[-2000:]
-    print(f"{tag}: {res[tag]:.2f} s wall", flush=True)
+    print(f"{tag}: {res[tag]:.2f} s wall", [l for l in r.stderr.splitlines() if l.startswith('[timing]')], flush=True)
 files = sorted(f for f in os.listdir(work + "/out_ref") if f.endswith(".fits"))
 assert files == sorted(f for f in os.listdir(work + "/out_gpu") if f.endswith(".fits"))
 worst = 0.0
