@@ -779,6 +779,8 @@ static int binned_alloc(slicer_handle *h)
   if (h->bin.rec_u)
     return 0;
   size_t slice = h->cfg.record_capacity ? h->cfg.record_capacity : ((size_t)1 << 28);
+  if (slice > ((size_t)1 << 31))
+    slice = (size_t)1 << 31; // record offsets are 32-bit
   size_t cap_particles = h->cfg.particle_capacity ? h->cfg.particle_capacity : slice;
   if (slice > cap_particles)
     slice = cap_particles;
