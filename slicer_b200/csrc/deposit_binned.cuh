@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
 }
 
 // K3: one CTA per (plane, tile) bin
+template <int MAS>
 __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
     tile_deposit_kernel(const __grid_constant__ PassParams P, const __grid_constant__ SortDev D, int ntile, int type, float const_mass)
 {
@@ -348,6 +349,18 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
   auto one = [&](float xs, float ys, float m) {
     const int gx = __float2int_rd(__fmul_rn(xs, L.npixf));
     const int gy = __float2int_rd(__fmul_rn(ys, L.npixf));
+    if (MAS == SLICER_MAS_NGP)
+    { // utilities.cpp:72-76: the whole mass goes to the nearest grid point, if it is inside the map
+      if (gx >= 0 && gx < nn && gy >= 0 && gy < nn)
+      {
+        const unsigned long long v = (unsigned long long)chain::to_fixed(m, L);
+        const int c = (gy - y0) * TW + gx - x0;
+        const unsigned vl = (unsigned)v, vh = (unsigned)(v >> 32);
+        const unsigned old = atomicAdd(lo + c, vl);
+        atomicAdd(hi + c, vh + ((old + vl < old) ? 1u : 0u));
+      }
+      return;
+    }
     const float sm = __fsqrt_rn(m);
     float wx[3], wy[3];
 #pragma unroll

@@ -759,7 +759,7 @@ static int binned_tiles(const PassParams &P) { return (P.pl[0].npix + binned::TI
 
 static bool use_binned(const slicer_handle *h, const PassParams &P, const SegmentDev &D)
 {
-  if (h->cfg.mas != SLICER_MAS_TSC || !P.fast || h->cfg.deposit_mode == SLICER_DEPOSIT_DIRECT)
+  if (!P.fast || h->cfg.deposit_mode == SLICER_DEPOSIT_DIRECT)
     return false;
   for (int q = 1; q < P.nplanes; q++)
     if (P.pl[q].npix != P.pl[0].npix)
@@ -844,7 +844,12 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
     binned::bin_scan_kernel<<<1, 1024, 0, h->compute>>>(Q);
     binned::bin_scatter_kernel<<<nregions, binned::SCATTER_THREADS, sizeof(binned::ScatterSmem), h->compute>>>(Q);
     if (!(h->debug & 4)) // measurement aid: SLICER_B200_DEBUG bit 2 skips the tile deposit
-      binned::tile_deposit_kernel<<<nbins, binned::DEPOSIT_THREADS, binned::TCELLS * 8, h->compute>>>(P, Q, nt, D.type, D.const_mass);
+    {
+      if (h->cfg.mas == SLICER_MAS_NGP)
+        binned::tile_deposit_kernel<SLICER_MAS_NGP><<<nbins, binned::DEPOSIT_THREADS, binned::TCELLS * 8, h->compute>>>(P, Q, nt, D.type, D.const_mass);
+      else
+        binned::tile_deposit_kernel<SLICER_MAS_TSC><<<nbins, binned::DEPOSIT_THREADS, binned::TCELLS * 8, h->compute>>>(P, Q, nt, D.type, D.const_mass);
+    }
     CU(cudaGetLastError());
     h->stats.launches += 5;
   }

@@ -200,15 +200,16 @@ def test_errors_are_loud():
         capi.Slicer(npix_max=32, max_planes=99)
 
 
+@pytest.mark.parametrize("mas", [capi.MAS_TSC, capi.MAS_NGP])
 @pytest.mark.parametrize("name", ["dm_face1", "hydro_multi"])
-def test_binned_deposit_golden(oracle, golden, name):
+def test_binned_deposit_golden(oracle, golden, name, mas):
     """The shared-memory tile path (records -> counting sort -> tiles) gives the same int64 maps (power-of-two maps)."""
     m = golden.meta[name]
     types, plane = golden.types(name), golden.plane(name)
-    got = run_plane(types, plane, m["npix"], capi.MAS_TSC, capi.KERNEL_PIPELINED, massarr=m["massarr"], hydro=bool(m["hydro"]),
+    got = run_plane(types, plane, m["npix"], mas, capi.KERNEL_PIPELINED, massarr=m["massarr"], hydro=bool(m["hydro"]),
                     deposit_mode=capi.DEPOSIT_BINNED)
     assert got["counts"].tolist() == m["counts"]
-    check_against_oracle(oracle, types, plane, m["npix"], got, False, 1.0)
+    check_against_oracle(oracle, types, plane, m["npix"], got, mas == capi.MAS_NGP, 1.0)
 
 
 @pytest.mark.parametrize("layout", [capi.LAYOUT_AOS, capi.LAYOUT_SOA])
@@ -224,6 +225,9 @@ def test_binned_deposit_slices_and_borders(oracle, npix, fov, cap, layout):
     got = run_plane(types, plane, npix, capi.MAS_TSC, capi.KERNEL_PIPELINED, layout=layout, massarr=[0, 0.8125, 0, 0, 0, 0],
                     deposit_mode=capi.DEPOSIT_BINNED, record_capacity=cap)
     res = check_against_oracle(oracle, types, plane, npix, got, False, 0.8125)
+    ngp = run_plane(types, plane, npix, capi.MAS_NGP, capi.KERNEL_PIPELINED, layout=layout, massarr=[0, 0.8125, 0, 0, 0, 0],
+                    deposit_mode=capi.DEPOSIT_BINNED, record_capacity=cap)
+    check_against_oracle(oracle, types, plane, npix, ngp, True, 0.8125)
     assert res["counts"][1] > 1000 and res["ingrid"][1] < res["counts"][1]  # some nearest grid points fall outside the map
 
 
