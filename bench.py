@@ -252,7 +252,7 @@ def ours(args, rank, world, local_rank):
 
     # ------------------------------------------------------------------ resident phase: `value` and the roofline
     s = capi.Slicer(npix_max=NPIX, max_planes=LENS_PER_SNAP, mas=capi.MAS_TSC, particle_capacity=npart + 64, device=local_rank,
-                    deposit_mode=args.deposit_mode)
+                    deposit_mode=args.deposit_mode, record_capacity=npart)
     if world > 1:
         uid = [capi.Slicer.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)

@@ -8,7 +8,7 @@ ng = int(os.environ.get("NG", "1024"))
 mas = capi.MAS_NGP if os.environ.get("MAS") == "NGP" else capi.MAS_TSC
 groups, raw = bench.c3_planes()
 n = ng ** 3
-s = capi.Slicer(npix_max=bench.NPIX, max_planes=4, mas=mas, particle_capacity=n + 64, record_capacity=int(os.environ.get('RECCAP', '0')),
+s = capi.Slicer(npix_max=bench.NPIX, max_planes=4, mas=mas, particle_capacity=n + 64, record_capacity=int(os.environ.get('RECCAP', str(n))),
                 deposit_mode=int(os.environ.get('DMODE', '0')))
 s.begin_snapshot(bench.BOX, [0, bench.MASS, 0, 0, 0, 0], False)
 s.stage_synthetic(1, n, 1000)
