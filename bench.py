@@ -222,6 +222,25 @@ def workload_config(n_gpus):
     }
 
 
+def bind_to_gpu_numa_node(index):
+    """Best effort: run this rank (and first-touch its pinned staging memory) on the CPUs NVML reports as local to its GPU,
+    so that 8 concurrent host->device streams do not cross the socket interconnect.  Returns the CPU list or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64 + 8)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 # ---- our arm -------------------------------------------------------------------------------------------------
 def ours(args, rank, world, local_rank):
     import torch
@@ -232,6 +251,7 @@ def ours(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU reference)")
     torch.cuda.set_device(local_rank)
+    affinity = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
 
@@ -391,7 +411,7 @@ def ours(args, rank, world, local_rank):
             "gpu_launches": launches, "clocks": clocks,
             "extra": {"per_group_kernel_ms": per_group, "stream_rate_particles_per_s": value, "ref_equiv_particle_passes_per_s": value * LENS_PER_SNAP,
                       "accepted_pairs_last_step": accepted, "kernel_ms_avg": kernel_ms,
-                      "gpu_launches_e2e": launches_e2e if e2e else None},
+                      "gpu_launches_e2e": launches_e2e if e2e else None, "cpu_affinity_rank0": affinity},
         }
         print(json.dumps(line))
     if world > 1:
