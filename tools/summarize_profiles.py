@@ -12,21 +12,22 @@ for r in rows:
     d[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
 L = list(launch.values())
 names = [l["name"] for l in L]
+# bench.py launches, after the synthetic-data kernel: 3 warm-up passes (groups 0,1,2), 9 timed passes (groups 0..8), then one extra
+# pass per group.  A pass is one direct K1 launch, or 1 slice (sparse) / 4 slices (dense) of (K1 + 5 bin kernels).  Slices of one
+# pass and consecutive one-slice passes look alike in the launch list, so the per-group slice counts are taken from the AUTO
+# rule of slicer_capi.cu (est_accept: direct < 1.5 % <= one slice < 12 % <= 2^28-particle slices) for this workload.
+SLICES = {0: 0, 1: 1, 2: 1, 3: 1, 4: 4, 5: 4, 6: 4, 7: 4, 8: 4}
+order = [0, 1, 2] + list(range(9))
 passes, i = [], 0
-while i < len(L):  # a pass = one direct K1 launch, or up to 4 slices of (K1 + 5 bin kernels)
-    if "deposit_pipelined" in names[i]:
-        if i + 1 < len(L) and "bin_histogram" in names[i + 1]:
-            grp, nsl = [], 0
-            while nsl < 4 and i + 1 < len(L) and "deposit_pipelined" in names[i] and "bin_histogram" in names[i + 1]:
-                grp += L[i:i + 6]
-                i += 6
-                nsl += 1
-            passes.append(grp)
-        else:
-            passes.append([L[i]])
-            i += 1
-    else:
-        i += 1
+while i < len(L) and "deposit_pipelined" not in names[i]:
+    i += 1
+for g in order:
+    n = 1 if SLICES[g] == 0 else 6 * SLICES[g]
+    grp = L[i:i + n]
+    assert "deposit_pipelined" in grp[0]["name"] and (n == 1 or "bin_histogram" in grp[1]["name"]), (g, [x["name"] for x in grp[:3]])
+    assert i + n >= len(L) or "deposit_pipelined" in names[i + n], (g, names[i + n])
+    passes.append(grp)
+    i += n
 timed = passes[3:12]  # bench: 3 warm-up passes, then the 9 timed ones
 summ, share = [], collections.defaultdict(float)
 for g, p in enumerate(timed):
@@ -61,7 +62,7 @@ want = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 out = [f"# Round {tag[1:]} — `ncu --set full` summary of the bench pass kernels", "",
        "Command (after the same command exited 0 without ncu): `ncu --set full --clock-control none --import-source on -k "
-       "regex:\"deposit_pipelined|bin_scatter|tile_deposit\" -s 38 -c 8 python bench.py --steps 9 --warmup 3 --no-cpu --no-e2e`", "",
+       "regex:\"deposit_pipelined|bin_scatter|tile_deposit\" -s 26 -c 8 python bench.py --steps 9 --warmup 3 --no-cpu --no-e2e`", "",
        "Captured launches: consecutive kernels of the timed light cone of the C3 workload (a binned slice = 2^28 particles, a direct pass = 2^30). "
        "Times under ncu are cold-cache and serialised.", "",
        "| metric | " + " | ".join(f"launch {i}" for i in range(len(rows) - 2)) + " |", "|---|" + "---|" * (len(rows) - 2)]
