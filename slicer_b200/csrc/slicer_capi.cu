@@ -577,7 +577,8 @@ static float float_floor(double d)
 }
 static bool is_f32(double d) { return (double)(float)d == d; }
 
-static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplanes, PassParams *P)
+// slot_of: accumulator slot (the caller's plane index) of planes[i]; nullptr => i (the usual case)
+static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplanes, PassParams *P, const int *slot_of = nullptr)
 {
   if (nplanes < 1 || nplanes > h->cfg.max_planes)
     return fail("slicer_deposit: nplanes %d outside 1..%d (max_planes)", nplanes, h->cfg.max_planes);
@@ -700,11 +701,12 @@ static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int npl
         if (L.nt > 20)
           L.nt = 0;
       }
-      L.acc = h->d_acc + (size_t)i * h->ntypes_alloc * h->npix2max;
-      L.counts = h->d_counts + (size_t)i * SLICER_NTYPES * 2;
+      const int slot = slot_of ? slot_of[i] : i;
+      L.acc = h->d_acc + (size_t)slot * h->ntypes_alloc * h->npix2max;
+      L.counts = h->d_counts + (size_t)slot * SLICER_NTYPES * 2;
       L.type_stride = h->cfg.per_type_maps ? h->npix2max : 0;
-      L.slot = i;
-      h->plane_npix[i] = d.npix;
+      L.slot = slot;
+      h->plane_npix[slot] = d.npix;
       {
         // fraction of a uniform snapshot this plane accepts: slab thickness x (field width / box)^2 at mid-distance
         const double w = L.T < 1.5 ? 2.0 * tan(L.T) * 0.5 * (minDist + maxDist) : 1.0;
@@ -765,21 +767,26 @@ static void fill_segment(const slicer_handle *h, const Segment &s, SegmentDev *D
 // ------------------------------------------------------------------------------------------------------------
 static int binned_tiles(const PassParams &P) { return (P.pl[0].npix + binned::TILE - 1) / binned::TILE; }
 
-static bool use_binned(const slicer_handle *h, const PassParams &P, const SegmentDev &D)
+// 0: direct map atomics; 1: binned, all planes in one go; 2: binned, but the planes' tiles exceed MAX_BINS: the caller
+// runs the binned pass over subsets of planes (each subset streams the particles again)
+static int use_binned(const slicer_handle *h, const PassParams &P, const SegmentDev &D)
 {
   if (!P.fast || h->cfg.deposit_mode == SLICER_DEPOSIT_DIRECT)
-    return false;
+    return 0;
   for (int q = 1; q < P.nplanes; q++)
     if (P.pl[q].npix != P.pl[0].npix)
-      return false;
+      return 0;
   const int nt = binned_tiles(P);
-  if ((long long)P.nplanes * nt * nt > binned::MAX_BINS)
-    return false;
+  if ((long long)nt * nt > binned::MAX_BINS)
+    return 0; // not even one plane fits
+  const bool split = (long long)P.nplanes * nt * nt > binned::MAX_BINS;
   if (h->cfg.deposit_mode == SLICER_DEPOSIT_BINNED)
-    return true;
+    return split ? 2 : 1;
   if (D.n < (1ull << 22))
-    return false;
-  return P.est_accept > (h->bin_slice_hint() >= D.n ? 0.015 : 0.03);
+    return 0;
+  if (split) // every subset re-reads the particles: worth it only when the map atomics would be many
+    return P.est_accept > 0.06 ? 2 : 0;
+  return P.est_accept > (h->bin_slice_hint() >= D.n ? 0.015 : 0.03) ? 1 : 0;
 }
 
 static int binned_alloc(slicer_handle *h)
@@ -923,10 +930,26 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
       continue;
     if (kernel == SLICER_KERNEL_PIPELINED)
     {
-      if (use_binned(h, P, D))
+      const int ub = use_binned(h, P, D);
+      if (ub == 1)
       {
         if (binned_pass(h, P, D))
           return 1;
+      }
+      else if (ub == 2)
+      { // large maps: as many planes per binned sub-pass as MAX_BINS allows
+        const int nt = binned_tiles(P);
+        const int per = binned::MAX_BINS / (nt * nt);
+        for (int p0 = 0; p0 < nplanes; p0 += per)
+        {
+          const int np = nplanes - p0 < per ? nplanes - p0 : per;
+          int slots[SLICER_MAX_PLANES];
+          for (int i = 0; i < np; i++)
+            slots[i] = p0 + i;
+          PassParams Ps;
+          if (build_pass(h, planes + p0, np, &Ps, slots) || binned_pass(h, Ps, D))
+            return 1;
+        }
       }
       else if (pipelined_launch(&h->pipe, h->cfg.mas, P, D, h->compute))
         return fail("pipelined launch failed: %s", cudaGetErrorString(cudaGetLastError()));

@@ -354,3 +354,29 @@ def test_large_scale_paths_agree():
         else:
             for a, b in zip(ref, got):
                 assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2] and a[3] == b[3] and np.array_equal(a[4], b[4])
+
+
+def test_binned_deposit_plane_subsets_for_huge_maps():
+    """8192^2 maps: 2500 tiles per plane, so three planes exceed the 4096 bins of one binned pass and are done in subsets;
+    the result must equal the direct path's (int64 maps and counters)."""
+    box = 128000.0
+    n = 300000
+    pos = synth.uniform_positions(n, box, 43)
+    npix = 8192
+    fov = 0.6
+    descs = [capi.plane_desc([1, -1, 1], 2, [0.25, 0.5, 0.75], 1.0, 128.0 + 32.0 * k, 128.0 + 32.0 * (k + 1), fov, npix) for k in range(3)]
+    out = {}
+    for mode in (capi.DEPOSIT_DIRECT, capi.DEPOSIT_BINNED):
+        with capi.Slicer(npix_max=npix, max_planes=3, mas=capi.MAS_TSC, particle_capacity=n + 64, deposit_mode=mode) as s:
+            s.begin_snapshot(box, [0, 1.5, 0, 0, 0, 0], False)
+            s.stage(1, pos)
+            s.deposit(descs)
+            out[mode] = []
+            for k in range(3):
+                _, c, g = s.fetch(k, -1, npix, want_map=False)
+                fx = s.fetch_fixed(k, -1, npix)
+                out[mode].append((c.tolist(), g.tolist(), int(fx.sum()), np.flatnonzero(fx.reshape(-1))[:50000].tolist(), fx.reshape(-1)[np.flatnonzero(fx.reshape(-1))[:50000]].tolist()))
+                del fx
+    for a, b in zip(out[capi.DEPOSIT_DIRECT], out[capi.DEPOSIT_BINNED]):
+        assert a == b
+    assert out[capi.DEPOSIT_DIRECT][0][0][1] > 10000
