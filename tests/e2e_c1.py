@@ -1,13 +1,13 @@
-"""Config C1/C2 end to end (BASELINE.json configs[0..1]): synthetic L128N256-shaped snapshots (ng^3 DM particles, box 128 Mpc/h,
+"""TEST INFRASTRUCTURE (not collected by pytest; run by hand on the GPU box) — Config C1/C2 end to end (BASELINE.json configs[0..1]): synthetic L128N256-shaped snapshots (ng^3 DM particles, box 128 Mpc/h,
 snapshots z = 0 .. 0.6), examples/InputParams.ini values (256^2 map, 2 deg, zs = 0.5, seeds -229/-230/-231), TSC.
 Runs the reference executable (oracle/_ref/SLICER_ref, 1 rank) and SLICER_b200 on the same files, times both (wall clock,
-including file I/O and FITS output), and compares every plane.  Measurement aid, not part of the product.
-usage: python tools/run_c1.py [ng=256] [numfiles=4] [workdir=/tmp/c1]"""
+including file I/O and FITS output), and compares every plane.  The reference executable is the checker here, as in tests/test_gpu_driver.py.
+usage: python tests/e2e_c1.py [ng=256] [numfiles=4] [workdir=/tmp/c1]"""
 import os, subprocess, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
 from slicer_b200 import host, synth
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 from test_gpu_driver import INI, read_shim_fits
 
 ng = int(sys.argv[1]) if len(sys.argv) > 1 else 256
