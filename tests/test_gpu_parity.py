@@ -380,3 +380,38 @@ def test_binned_deposit_plane_subsets_for_huge_maps():
     for a, b in zip(out[capi.DEPOSIT_DIRECT], out[capi.DEPOSIT_BINNED]):
         assert a == b
     assert out[capi.DEPOSIT_DIRECT][0][0][1] > 10000
+
+
+FUZZ_SEEDS = list(range(24))
+
+
+@pytest.mark.parametrize("seed", FUZZ_SEEDS)
+def test_randomised_plane_parameters(oracle, seed):
+    """Seeded fuzz over everything a plane descriptor carries: box size (float-exact or not), signs, face, centre,
+    rcase, slab edges, field of view from 0.03 to 1.3 rad (small-angle series and the generic libm-equivalent
+    branch), map sizes that are not powers of two, replication, TSC/NGP, both kernels and both deposit modes."""
+    rng = np.random.default_rng(1000 + seed)
+    box = float(rng.choice([128000.0, 100000.0, 75000.0, 250000.0, 123456.789, 62500.0]))
+    n = int(rng.integers(20000, 90000))
+    pos = synth.uniform_positions(n, box, 900 + seed)
+    if seed % 5 == 0:  # particles exactly on the box faces and at the origin
+        pos[:64] = 0.0
+        pos[64:128, 0] = np.float32(box)
+        pos[128:192, 2] = np.nextafter(np.float32(box), np.float32(0))
+    mass = float(rng.choice([1.0375, 0.0123, 57.25]))
+    types = [dict(type=1, raw=pos, const_mass=mass)]
+    rcase = float(rng.integers(0, 4))
+    lo = rcase + float(rng.uniform(0.0, 0.7))
+    hi = min(lo + float(rng.uniform(0.05, 0.6)), rcase + 1.0)
+    nrep = int(rng.integers(0, 2)) if seed % 3 == 0 else 0
+    fov = float(rng.choice([0.03, 0.0872664626, 0.2, 0.45, 0.8, 1.3]))
+    npix = int(rng.choice([64, 100, 128, 333, 512, 1000]))
+    plane = dict(boxsize=box, sgn=[int(v) for v in rng.choice([-1, 1], 3)], face=int(rng.integers(1, 7)),
+                 centre=[float(np.float32(v)) for v in rng.uniform(0, 1, 3)], rcase=rcase, ld=lo * box / 1e3, ld2=hi * box / 1e3,
+                 nrepperp=nrep, fovradiants=fov)
+    mas = capi.MAS_TSC if seed % 2 == 0 else capi.MAS_NGP
+    kernel = capi.KERNEL_PIPELINED if seed % 4 != 3 else capi.KERNEL_SIMPLE
+    mode = [capi.DEPOSIT_AUTO, capi.DEPOSIT_DIRECT, capi.DEPOSIT_BINNED][seed % 3] if kernel == capi.KERNEL_PIPELINED else capi.DEPOSIT_AUTO
+    got = run_plane(types, plane, npix, mas, kernel, massarr=[0, mass, 0, 0, 0, 0], deposit_mode=mode,
+                    record_capacity=(4 * n if mode == capi.DEPOSIT_BINNED else 0))
+    check_against_oracle(oracle, types, plane, npix, got, mas == capi.MAS_NGP, mass, strict_float=False)
