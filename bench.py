@@ -48,8 +48,9 @@ NGROUPS = 9                  # full randomisation groups of the zs=1 light cone 
 LENS_PER_SNAP = 4
 
 
-def c3_planes():
-    """Plane descriptors of the C3 light cone, group by group (plan arithmetic of buildPlanes/randomizeBox)."""
+def c3_planes(BOX=BOX, NPIX=NPIX, FOV_DEG=FOV_DEG, NGROUPS=NGROUPS):
+    """Plane descriptors of the C3 light cone, group by group (plan arithmetic of buildPlanes/randomizeBox).
+    The keyword arguments exist for tools/probe_groups.py (other geometries, e.g. C5's 8192^2 maps); bench.py uses the defaults."""
     from slicer_b200 import capi, plan
 
     nplanes = NGROUPS * LENS_PER_SNAP

@@ -31,7 +31,7 @@ namespace binned
 constexpr int TILE = SLICER_TILE;  // interior cells per tile side (166: one 1024-thread CTA per SM owns 226 KB; 116: two CTAs)
 constexpr int TW = TILE + 2;       // + 1-cell halo for the 3x3 stencil
 constexpr int TCELLS = TW * TW;    // 28,224 cells x 8 B = 225,792 B of shared memory
-constexpr int MAX_BINS = 4096;     // planes x tiles^2 per pass (4 planes of 4096^2, 16 planes of 2048^2)
+constexpr int MAX_BINS = 5120; // bins per sort window: 3 tables of MAX_BINS words + the 16K-record batch fill the scatter kernel's shared memory
 constexpr int SCATTER_THREADS = 1024;
 constexpr int DEPOSIT_THREADS = 1024 / SLICER_TILE_CTAS;
 
@@ -53,7 +53,8 @@ struct SortDev
   const unsigned *region_count;
   unsigned long long region_cap;
   int nregions;
-  int nbins;
+  int nbins;  // bins sorted by this round of K2/K3: global bins [bin_lo, bin_lo + nbins); records of other bins are skipped
+  int bin_lo; // (maps whose planes x tiles exceed MAX_BINS are deposited window by window from ONE set of records)
   unsigned *region_hist; // [nbins][nregions]: records of region r in bin b, then (after the scan) their offset within the bin
   unsigned *bin_count;   // [nbins]
   unsigned *bin_start;   // [nbins + 1]
@@ -97,7 +98,11 @@ __global__ void __launch_bounds__(SCATTER_THREADS) bin_histogram_kernel(const __
   const int r = blockIdx.x;
   const unsigned n = D.region_count[r];
   for_each_key(D.key_u + (unsigned long long)r * D.region_cap, n, threadIdx.x, SCATTER_THREADS,
-               [&](unsigned, unsigned k) { atomicAdd(&hist[k], 1u); });
+               [&](unsigned, unsigned k) {
+                 k -= (unsigned)D.bin_lo;
+                 if (k < (unsigned)D.nbins)
+                   atomicAdd(&hist[k], 1u);
+               });
   __syncthreads();
   for (int i = threadIdx.x; i < D.nbins; i += SCATTER_THREADS)
     D.region_hist[(size_t)i * D.nregions + r] = hist[i];
@@ -193,22 +198,28 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
 // addresses.  No global atomics; the bin layout is deterministic up to the order inside a (batch, bin) run.
 constexpr int SCATTER_BATCH = 16384;
 constexpr int SCATTER_PER = SCATTER_BATCH / SCATTER_THREADS; // records per thread per batch
+// NB = table size: MAX_BINS, or SMALL_BINS for the usual few-plane 2048^2 passes (a shorter scan per batch)
+constexpr int SMALL_BINS = 4096;
+template <int NB>
 struct ScatterSmem
 {
   float2 rec[SCATTER_BATCH];
   unsigned short bin[SCATTER_BATCH];
-  unsigned cnt[MAX_BINS];    // records of the batch per bin, then running rank
-  unsigned lstart[MAX_BINS]; // first sorted slot of the bin in this batch
-  unsigned gcur[MAX_BINS];   // next free global slot of the bin for this region
+  unsigned cnt[NB];    // records of the batch per bin, then running rank
+  unsigned lstart[NB]; // first sorted slot of the bin in this batch
+  unsigned gcur[NB];   // next free global slot of the bin for this region
   unsigned wsum[SCATTER_THREADS / 32];
+  unsigned ntot; // records of the batch inside the bin window
 };
 
+// WIN: the sort covers a window of the bins only (maps with more than MAX_BINS plane-tiles), other records are skipped
+template <int NB, bool WIN>
 __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const __grid_constant__ SortDev D)
 {
   extern __shared__ __align__(16) unsigned char scatter_raw[];
-  ScatterSmem &sm = *reinterpret_cast<ScatterSmem *>(scatter_raw);
+  ScatterSmem<NB> &sm = *reinterpret_cast<ScatterSmem<NB> *>(scatter_raw);
   float *smass = reinterpret_cast<float *>(sm.rec); // per-particle masses reuse the record staging in a second sweep
-  constexpr int PER = MAX_BINS / SCATTER_THREADS; // bins per thread in the scan
+  constexpr int PER = NB / SCATTER_THREADS; // bins per thread in the scan
   const int r = blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const unsigned n = D.region_count[r];
@@ -216,6 +227,8 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
     return;
   for (int i = t; i < D.nbins; i += SCATTER_THREADS)
     sm.gcur[i] = D.bin_start[i] + D.region_hist[(size_t)i * D.nregions + r];
+  for (int i = D.nbins + t; i < NB; i += SCATTER_THREADS)
+    sm.cnt[i] = 0; // never incremented: the batch scan runs over all MAX_BINS entries
   const unsigned long long off = (unsigned long long)r * D.region_cap;
   const unsigned short *key = D.key_u + off;
   const float2 *rec = D.rec_u + off;
@@ -224,7 +237,7 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
   {
     const unsigned nb = min(n - base, (unsigned)SCATTER_BATCH);
     for (int i = t; i < D.nbins; i += SCATTER_THREADS)
-      sm.cnt[i] = 0; // bins >= nbins hold garbage: it only reaches prefix sums of bins that do not exist
+      sm.cnt[i] = 0;
     __syncthreads();
     // 1. coalesced loads, rank inside (batch, bin)
     unsigned k[SCATTER_PER]; // bin | rank << 16 (rank < SCATTER_BATCH = 2^13)
@@ -236,8 +249,10 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
       k[j] = 0xffffffffu;
       if (i < nb)
       {
-        k[j] = key[base + i];
-        e[j] = rec[base + i];
+        const unsigned kk = (unsigned)key[base + i] - (WIN ? (unsigned)D.bin_lo : 0u);
+        e[j] = rec[base + i]; // unconditionally: a load that waits for the key compare would serialise the two latencies
+        if (!WIN || kk < (unsigned)D.nbins)
+          k[j] = kk;
       }
     }
 #pragma unroll
@@ -286,7 +301,10 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
       sm.lstart[PER * t + j] = ex;
       ex += c[j];
     }
+    if (WIN && t == SCATTER_THREADS - 1)
+      sm.ntot = ex;
     __syncthreads();
+    const unsigned ntot = WIN ? sm.ntot : nb;
     // 3. sorted order in shared memory
 #pragma unroll
     for (int j = 0; j < SCATTER_PER; j++)
@@ -298,7 +316,7 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
       }
     __syncthreads();
     // 4. write-out: slot i of the sorted batch -> gcur[bin] + (i - lstart[bin]); runs are contiguous in memory
-    for (unsigned i = t; i < nb; i += SCATTER_THREADS)
+    for (unsigned i = t; i < ntot; i += SCATTER_THREADS)
     {
       const unsigned b = sm.bin[i];
       const unsigned dst = sm.gcur[b] + (i - sm.lstart[b]);
@@ -312,7 +330,7 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
         if (k[j] != 0xffffffffu)
           smass[sm.lstart[k[j] & 0xffffu] + (k[j] >> 16)] = mass[base + j * SCATTER_THREADS + t];
       __syncthreads();
-      for (unsigned i = t; i < nb; i += SCATTER_THREADS)
+      for (unsigned i = t; i < ntot; i += SCATTER_THREADS)
       {
         const unsigned b = sm.bin[i];
         D.mass_s[sm.gcur[b] + (i - sm.lstart[b])] = smass[i];
@@ -325,6 +343,20 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
   }
 }
 
+static inline cudaError_t prepare_bin_scatter()
+{
+  cudaError_t e = cudaFuncSetAttribute(bin_scatter_kernel<SMALL_BINS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<SMALL_BINS>));
+  return e != cudaSuccess ? e : cudaFuncSetAttribute(bin_scatter_kernel<MAX_BINS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<MAX_BINS>));
+}
+
+static inline void launch_bin_scatter(const SortDev &Q, bool windowed, cudaStream_t stream)
+{
+  if (!windowed && Q.nbins <= SMALL_BINS)
+    bin_scatter_kernel<SMALL_BINS, false><<<Q.nregions, SCATTER_THREADS, sizeof(ScatterSmem<SMALL_BINS>), stream>>>(Q);
+  else
+    bin_scatter_kernel<MAX_BINS, true><<<Q.nregions, SCATTER_THREADS, sizeof(ScatterSmem<MAX_BINS>), stream>>>(Q);
+}
+
 // K3: one CTA per (plane, tile) bin
 template <int MAS>
 __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
@@ -333,10 +365,10 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
   extern __shared__ __align__(16) unsigned tile_smem[];
   unsigned *lo = tile_smem;
   unsigned *hi = tile_smem + TCELLS;
-  const int b = blockIdx.x;
-  const unsigned r0 = D.bin_start[b], r1 = D.bin_start[b + 1];
+  const unsigned r0 = D.bin_start[blockIdx.x], r1 = D.bin_start[blockIdx.x + 1];
   if (r0 == r1)
     return;
+  const int b = blockIdx.x + D.bin_lo;
   const int q = b / (ntile * ntile);
   const int tb = b - q * ntile * ntile;
   const int ty = tb / ntile, tx = tb - ty * ntile;

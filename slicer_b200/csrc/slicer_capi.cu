@@ -767,8 +767,8 @@ static void fill_segment(const slicer_handle *h, const Segment &s, SegmentDev *D
 // ------------------------------------------------------------------------------------------------------------
 static int binned_tiles(const PassParams &P) { return (P.pl[0].npix + binned::TILE - 1) / binned::TILE; }
 
-// 0: direct map atomics; 1: binned, all planes in one go; 2: binned, but the planes' tiles exceed MAX_BINS: the caller
-// runs the binned pass over subsets of planes (each subset streams the particles again)
+// 0: direct map atomics; 1: binned.  When the planes' tiles exceed MAX_BINS (8192^2 maps) the records are still
+// produced once; the sort and the tile deposit then run window by window over the bins (binned_pass).
 static int use_binned(const slicer_handle *h, const PassParams &P, const SegmentDev &D)
 {
   if (!P.fast || h->cfg.deposit_mode == SLICER_DEPOSIT_DIRECT)
@@ -777,16 +777,16 @@ static int use_binned(const slicer_handle *h, const PassParams &P, const Segment
     if (P.pl[q].npix != P.pl[0].npix)
       return 0;
   const int nt = binned_tiles(P);
-  if ((long long)nt * nt > binned::MAX_BINS)
-    return 0; // not even one plane fits
-  const bool split = (long long)P.nplanes * nt * nt > binned::MAX_BINS;
+  if ((long long)P.nplanes * nt * nt > 65536)
+    return 0; // record keys are 16 bits (16 planes of 10624^2 pixels still fit)
   if (h->cfg.deposit_mode == SLICER_DEPOSIT_BINNED)
-    return split ? 2 : 1;
+    return 1;
   if (D.n < (1ull << 22))
     return 0;
-  if (split) // every subset re-reads the particles: worth it only when the map atomics would be many
-    return P.est_accept > 0.06 ? 2 : 0;
-  return P.est_accept > (h->bin_slice_hint() >= D.n ? 0.015 : 0.03) ? 1 : 0;
+  // measured break-even: 3 % of the snapshot accepted; 1.5 % when one slice holds the whole batch, or when
+  // the planes' accumulators are several times the L2 (> 256 MiB, e.g. 4096^2 and 8192^2 maps: the direct path's atomics go to HBM)
+  const bool big_maps = (size_t)P.nplanes * P.pl[0].npix * P.pl[0].npix * sizeof(unsigned long long) > ((size_t)256 << 20);
+  return P.est_accept > (h->bin_slice_hint() >= D.n || big_maps ? 0.015 : 0.03) ? 1 : 0;
 }
 
 static int binned_alloc(slicer_handle *h)
@@ -823,7 +823,8 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
   // few accepted particles: one slice as large as the buffers allow (the per-slice fixed costs dominate);
   // many: 2^28-particle slices (measured optimum at 25-55 % acceptance)
   size_t slice = h->bin.slice;
-  if (P.est_accept >= 0.12 && slice > ((size_t)1 << 28))
+  // (not for maps of several bin windows: their tiles are sparsely filled, the per-tile zero + flush dominates)
+  if (P.est_accept >= 0.12 && nbins <= binned::MAX_BINS && slice > ((size_t)1 << 28))
     slice = (size_t)1 << 28;
   for (unsigned long long off = 0; off < D.n; off += slice)
   {
@@ -852,6 +853,7 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
     Q.region_cap = E.region_cap;
     Q.nregions = nregions;
     Q.nbins = nbins;
+    Q.bin_lo = 0;
     Q.region_hist = h->bin.region_hist;
     Q.bin_count = h->bin.bin_count;
     Q.bin_start = h->bin.bin_start;
@@ -859,19 +861,27 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
     Q.mass_s = D.mass ? h->bin.mass_s : nullptr;
     if (pipelined_launch_emit(grid, P, S, E, h->compute))
       return fail("record kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    binned::bin_histogram_kernel<<<nregions, binned::SCATTER_THREADS, 0, h->compute>>>(Q);
-    binned::bin_region_scan_kernel<<<nbins, 1024, 0, h->compute>>>(Q);
-    binned::bin_scan_kernel<<<1, 1024, 0, h->compute>>>(Q);
-    binned::bin_scatter_kernel<<<nregions, binned::SCATTER_THREADS, sizeof(binned::ScatterSmem), h->compute>>>(Q);
-    if (!(h->debug & 4)) // measurement aid: SLICER_B200_DEBUG bit 2 skips the tile deposit
+    const int nwin = (nbins + binned::MAX_BINS - 1) / binned::MAX_BINS;
+    const int wbins = (nbins + nwin - 1) / nwin;
+    for (int lo = 0; lo < nbins; lo += wbins)
     {
-      if (h->cfg.mas == SLICER_MAS_NGP)
-        binned::tile_deposit_kernel<SLICER_MAS_NGP><<<nbins, binned::DEPOSIT_THREADS, binned::TCELLS * 8, h->compute>>>(P, Q, nt, D.type, D.const_mass);
-      else
-        binned::tile_deposit_kernel<SLICER_MAS_TSC><<<nbins, binned::DEPOSIT_THREADS, binned::TCELLS * 8, h->compute>>>(P, Q, nt, D.type, D.const_mass);
+      Q.bin_lo = lo;
+      Q.nbins = nbins - lo < wbins ? nbins - lo : wbins;
+      binned::bin_histogram_kernel<<<nregions, binned::SCATTER_THREADS, 0, h->compute>>>(Q);
+      binned::bin_region_scan_kernel<<<Q.nbins, 1024, 0, h->compute>>>(Q);
+      binned::bin_scan_kernel<<<1, 1024, 0, h->compute>>>(Q);
+      binned::launch_bin_scatter(Q, nwin > 1, h->compute);
+      if (!(h->debug & 4)) // measurement aid: SLICER_B200_DEBUG bit 2 skips the tile deposit
+      {
+        if (h->cfg.mas == SLICER_MAS_NGP)
+          binned::tile_deposit_kernel<SLICER_MAS_NGP><<<Q.nbins, binned::DEPOSIT_THREADS, binned::TCELLS * 8, h->compute>>>(P, Q, nt, D.type, D.const_mass);
+        else
+          binned::tile_deposit_kernel<SLICER_MAS_TSC><<<Q.nbins, binned::DEPOSIT_THREADS, binned::TCELLS * 8, h->compute>>>(P, Q, nt, D.type, D.const_mass);
+      }
+      h->stats.launches += 4;
     }
     CU(cudaGetLastError());
-    h->stats.launches += 5;
+    h->stats.launches += 1;
   }
   return 0;
 }
@@ -935,21 +945,6 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
       {
         if (binned_pass(h, P, D))
           return 1;
-      }
-      else if (ub == 2)
-      { // large maps: as many planes per binned sub-pass as MAX_BINS allows
-        const int nt = binned_tiles(P);
-        const int per = binned::MAX_BINS / (nt * nt);
-        for (int p0 = 0; p0 < nplanes; p0 += per)
-        {
-          const int np = nplanes - p0 < per ? nplanes - p0 : per;
-          int slots[SLICER_MAX_PLANES];
-          for (int i = 0; i < np; i++)
-            slots[i] = p0 + i;
-          PassParams Ps;
-          if (build_pass(h, planes + p0, np, &Ps, slots) || binned_pass(h, Ps, D))
-            return 1;
-        }
       }
       else if (pipelined_launch(&h->pipe, h->cfg.mas, P, D, h->compute))
         return fail("pipelined launch failed: %s", cudaGetErrorString(cudaGetLastError()));

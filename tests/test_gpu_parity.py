@@ -356,9 +356,10 @@ def test_large_scale_paths_agree():
                 assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2] and a[3] == b[3] and np.array_equal(a[4], b[4])
 
 
-def test_binned_deposit_plane_subsets_for_huge_maps():
-    """8192^2 maps: 2500 tiles per plane, so three planes exceed the 4096 bins of one binned pass and are done in subsets;
-    the result must equal the direct path's (int64 maps and counters)."""
+def test_binned_deposit_bin_windows_for_huge_maps():
+    """8192^2 maps: 2500 tiles per plane, so three planes exceed the 4096 bins one sort can hold: the records are produced
+    once and sorted / deposited in two windows of 3750 bins (a window boundary inside a plane).  The result must equal
+    the direct path's (int64 maps and counters)."""
     box = 128000.0
     n = 300000
     pos = synth.uniform_positions(n, box, 43)
