@@ -1,6 +1,7 @@
 // host_capi.cpp — C entry points over the C++ host layer, for the Python tests (ctypes).  Thin marshalling only.
 #include "slicer_host.h"
 
+#include <chrono>
 #include <cstring>
 
 using namespace slicer;
@@ -142,6 +143,24 @@ extern "C"
       memcpy(pos, s.pos, s.ntotal * 12);
     if (mass)
       memcpy(mass, s.mass, s.ntotal * 4);
+    return 0;
+  }
+
+  // measurement aid (tools/probe_reader.py): best wall time of `repeats` readSubFile calls into one (pinned) buffer
+  int shost_time_read_subfile(const char *file, int hydro, int pinned, int repeats, double *best_seconds, long long *bytes)
+  {
+    SubFile s;
+    *best_seconds = 1e30;
+    for (int r = 0; r < repeats; r++)
+    {
+      const auto t0 = std::chrono::steady_clock::now();
+      if (readSubFile(file, hydro != 0, s, pinned != 0))
+        return 1;
+      const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      if (dt < *best_seconds)
+        *best_seconds = dt;
+    }
+    *bytes = (long long)s.ntotal * 12;
     return 0;
   }
 

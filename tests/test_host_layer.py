@@ -124,3 +124,29 @@ def test_glibc_rand_restatement_matches_libc():
         libc_srand(seed)
         want = [libc_rand() for _ in range(3000)]
         assert host.glibc_rand(seed, 3000).tolist() == want
+
+
+def test_reader_parallel_bulk_read(tmp_path):
+    """Payloads >= 8 MiB are read by several threads (pread on disjoint ranges): same bytes as the plain read
+    (SLICER_B200_IO_THREADS=1, in a fresh process because the thread count is latched), for POS and MASS blocks."""
+    import subprocess, sys, textwrap
+    box = 100000.0
+    n0, n1 = 2_300_000, 1_000_003  # gas MASS block 9.2 MB, POS block 39.6 MB: not multiples of the 1 MiB chunk rounding
+    pos = {0: synth.uniform_positions(n0, box, 11), 1: synth.uniform_positions(n1, box, 12)}
+    masses = {0: (np.arange(n0, dtype=np.float32) % 977) + 1}
+    base = str(tmp_path / "snap_big")
+    synth.write_snapshot(base, pos, [0, 0.5, 0, 0, 0, 0], 0.1, box, numfiles=1, masses=masses)
+    s = host.read_subfile(f"{base}.0", True, n0 + n1 + 10)
+    assert s["npart"].tolist() == [n0, n1, 0, 0, 0, 0]
+    assert np.array_equal(s["pos"][:n0], pos[0]) and np.array_equal(s["pos"][n0:], pos[1])
+    assert np.array_equal(s["mass"][:n0], masses[0]) and not s["mass"][n0:].any()
+    code = textwrap.dedent(f"""
+        import sys, zlib, numpy as np
+        sys.path.insert(0, {str(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))!r})
+        from slicer_b200 import host
+        s = host.read_subfile({base + '.0'!r}, True, {n0 + n1 + 10})
+        print(zlib.crc32(s['pos'].tobytes()), zlib.crc32(s['mass'].tobytes()))
+    """)
+    import zlib
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SLICER_B200_IO_THREADS="1"), capture_output=True, text=True, check=True)
+    assert out.stdout.split() == [str(zlib.crc32(s["pos"].tobytes())), str(zlib.crc32(s["mass"].tobytes()))]
