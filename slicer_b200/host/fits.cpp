@@ -95,19 +95,17 @@ void writeFitsImage(const std::string &file, const float *map, int npix, const s
   hdr.resize((hdr.size() + 2879) / 2880 * 2880, ' ');
   bool ok = fwrite(hdr.data(), 1, hdr.size(), f) == hdr.size();
   const size_t n = (size_t)npix * npix;
-  std::vector<unsigned char> row((size_t)npix * 4);
+  std::vector<uint32_t> row((size_t)npix); // FITS is big-endian: one vectorisable byte swap per row, one write per row
   for (int gy = 0; gy < npix && ok; gy++)
   {
+    const float *src = map + (size_t)npix * gy;
     for (int gx = 0; gx < npix; gx++)
     {
       uint32_t u;
-      memcpy(&u, &map[(size_t)gx + (size_t)npix * gy], 4);
-      row[4 * gx + 0] = u >> 24;
-      row[4 * gx + 1] = u >> 16;
-      row[4 * gx + 2] = u >> 8;
-      row[4 * gx + 3] = u;
+      memcpy(&u, src + gx, 4);
+      row[gx] = __builtin_bswap32(u);
     }
-    ok = fwrite(row.data(), 1, row.size(), f) == row.size();
+    ok = fwrite(row.data(), 4, row.size(), f) == row.size();
   }
   const size_t pad = (2880 - (n * 4) % 2880) % 2880;
   if (ok && pad)
