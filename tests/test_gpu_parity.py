@@ -449,3 +449,71 @@ def test_two_handles_on_one_device_from_two_threads(oracle):
     assert not err, err
     for i, (pos, plane, mas, mode) in enumerate(jobs):
         check_against_oracle(oracle, [dict(type=1, raw=pos, const_mass=1.0375)], plane, 256, out[i], mas == capi.MAS_NGP, 1.0375, strict_float=False)
+
+
+def _consecutive_floats(centre, k):
+    """2k+1 consecutive float32 values around `centre`."""
+    c = np.float32(centre)
+    i = c.view(np.int32) if isinstance(c, np.ndarray) else np.array(c, np.float32).view(np.int32)
+    return (int(i) + np.arange(-k, k + 1, dtype=np.int64)).astype(np.int32).view(np.float32)
+
+
+@pytest.mark.parametrize("mas", [capi.MAS_TSC, capi.MAS_NGP])
+@pytest.mark.parametrize("kernel,mode", [(capi.KERNEL_SIMPLE, capi.DEPOSIT_AUTO), (capi.KERNEL_PIPELINED, capi.DEPOSIT_DIRECT),
+                                         (capi.KERNEL_PIPELINED, capi.DEPOSIT_BINNED)])
+def test_decision_boundaries_float_by_float(oracle, mas, kernel, mode):
+    """Every decision of the chain, probed with runs of CONSECUTIVE float32 inputs straddling it: the slab edges
+    (float z against double minDist/maxDist, densitymaps.cpp:374), the field-of-view edge (|ra|,|dec| <= fov(1+2/npix)/2,
+    :383), pixel edges (floor(x/dl), utilities.cpp:55-60) and the box wrap.  Counts and int64 maps must equal the oracle's."""
+    box = 100000.0  # not a power of two: raw/box rounds
+    npix = 256
+    fov = 0.3
+    lo, hi = 0.2371, 0.5113  # slab edges in box units, not float-representable
+    plane = dict(boxsize=box, sgn=[1, 1, 1], face=1, centre=[0.0, 0.0, 0.0], rcase=0.0, ld=lo * box / 1e3, ld2=hi * box / 1e3, nrepperp=0,
+                 fovradiants=fov)
+    k = 300
+    rows = []
+    mid = np.float32(0.5 * box)
+    # 1. slab edges: z sweeps float by float across minDist and maxDist, on the optical axis (x = y = box/2)
+    for edge in (lo, hi):
+        z = _consecutive_floats(edge * box, k)
+        rows.append(np.stack([np.full_like(z, mid), np.full_like(z, mid), z], 1))
+    # 2. field-of-view edge in dec (x) and in ra (y) at a fixed depth
+    zc = np.float32(0.4 * box)
+    T = fov * (1 + 2.0 / npix) * 0.5
+    for axis in (0, 1):
+        for sign in (-1, 1):
+            # dec = asin(X/d), ra = atan(Y/Z): solve for the raw coordinate on the edge, then sweep around it
+            off = (np.tan(T) if axis == 1 else np.sin(T) / np.sqrt(1 - np.sin(T) ** 2)) * 0.4
+            v = _consecutive_floats((0.5 + sign * off) * box, k)
+            r = np.stack([np.full_like(v, mid), np.full_like(v, mid), np.full_like(v, zc)], 1)
+            r[:, axis] = v
+            rows.append(r)
+    # 3. pixel edges: x sweeps across the boundary between two pixels near the map centre and near its border
+    for frac in (0.5, 0.5 + 37.0 / npix, 1.0 / npix, 1.0 - 1.0 / npix):
+        ang = (frac - 0.5) * fov
+        v = _consecutive_floats((0.5 + np.tan(ang) * 0.4) * box, k)
+        r = np.stack([v, np.full_like(v, mid), np.full_like(v, zc)], 1)
+        rows.append(r)
+    pos = np.ascontiguousarray(np.concatenate(rows).astype(np.float32))
+    types = [dict(type=1, raw=pos, const_mass=0.77)]
+    got = run_plane(types, plane, npix, mas, kernel, massarr=[0, 0.77, 0, 0, 0, 0], deposit_mode=mode, record_capacity=1 << 16)
+    res = check_against_oracle(oracle, types, plane, npix, got, mas == capi.MAS_NGP, 0.77, strict_float=False)
+    n_acc = int(res["counts"][1])
+    assert 0.2 * len(pos) < n_acc < 0.8 * len(pos)  # the sweeps really straddle the decisions
+    # 4. the box wraps (gadget2io.cpp:209-220, 258-269): raw coordinates float by float around 0 and around the box size, with a
+    # centre that brings the wrapped particle back onto the optical axis inside the slab (x' = y' = 0.5, z' = 0.4)
+    plane_w = dict(plane, centre=[0.5, 0.5, 0.6])
+    rows = []
+    for axis in range(3):
+        for edge in (0.0, box):
+            v = _consecutive_floats(edge, k)
+            v = v[np.isfinite(v) & (v >= 0)]  # the reference aborts on negative box coordinates (densitymaps.cpp:314-345)
+            r = np.zeros((len(v), 3), np.float32)
+            r[:, axis] = v
+            rows.append(r)
+    pos = np.ascontiguousarray(np.concatenate(rows))
+    types = [dict(type=1, raw=pos, const_mass=0.77)]
+    got = run_plane(types, plane_w, npix, mas, kernel, massarr=[0, 0.77, 0, 0, 0, 0], deposit_mode=mode, record_capacity=1 << 16)
+    res = check_against_oracle(oracle, types, plane_w, npix, got, mas == capi.MAS_NGP, 0.77, strict_float=False)
+    assert int(res["counts"][1]) > 0.9 * len(pos)
