@@ -517,3 +517,23 @@ def test_decision_boundaries_float_by_float(oracle, mas, kernel, mode):
     got = run_plane(types, plane_w, npix, mas, kernel, massarr=[0, 0.77, 0, 0, 0, 0], deposit_mode=mode, record_capacity=1 << 16)
     res = check_against_oracle(oracle, types, plane_w, npix, got, mas == capi.MAS_NGP, 0.77, strict_float=False)
     assert int(res["counts"][1]) > 0.9 * len(pos)
+
+
+def test_seven_million_accepted_particles_bit_exact(oracle):
+    """Statistical weight for the deviation budget of DESIGN.md §5 (the device's asin/atan series against glibc's): 2^23 particles,
+    6.7 million of them accepted, i.e. 1.3e7 map coordinates narrowed to float.  The int64 maps of the direct and the binned path
+    must both equal the oracle's (libm) bit for bit."""
+    box = 128000.0
+    n = 1 << 23
+    pos = synth.uniform_positions(n, box, 7)
+    types = [dict(type=1, raw=pos, const_mass=1.0)]
+    plane = dict(boxsize=box, sgn=[1, -1, 1], face=3, centre=[0.25, 0.5, 0.75], rcase=1.0, ld=128.0, ld2=256.0, nrepperp=0, fovradiants=0.6)
+    npix = 1024
+    res = None
+    for mode in (capi.DEPOSIT_DIRECT, capi.DEPOSIT_BINNED):
+        got = run_plane(types, plane, npix, capi.MAS_TSC, capi.KERNEL_PIPELINED, massarr=[0, 1.0, 0, 0, 0, 0], deposit_mode=mode)
+        if res is None:
+            res = oracle.plane_from_particles(types, plane, npix, frac_bits=got["frac_bits"])
+            assert res["counts"][1] > 6_000_000
+        assert got["counts"].tolist() == res["counts"].tolist() and got["ingrid"].tolist() == res["ingrid"].tolist()
+        assert np.array_equal(got["fixed"][1], res["fixed"][1])
