@@ -60,6 +60,7 @@ struct SortDev
   unsigned *bin_start;   // [nbins + 1]
   float2 *rec_s;
   float *mass_s;
+  unsigned long long capacity; // records rec_u/rec_s/key_u can hold (bounds checks of the checked build)
 };
 
 __device__ __forceinline__ int bin_of(int q, int gx, int gy, int nn, int ntile)
@@ -311,6 +312,7 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
       if (k[j] != 0xffffffffu)
       {
         const unsigned lp = sm.lstart[k[j] & 0xffffu] + (k[j] >> 16);
+        SLICER_CHECK((k[j] & 0xffffu) < (unsigned)D.nbins && lp < (unsigned)SCATTER_BATCH);
         sm.rec[lp] = e[j];
         sm.bin[lp] = (unsigned short)(k[j] & 0xffffu);
       }
@@ -320,6 +322,7 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
     {
       const unsigned b = sm.bin[i];
       const unsigned dst = sm.gcur[b] + (i - sm.lstart[b]);
+      SLICER_CHECK(b < (unsigned)D.nbins && dst >= D.bin_start[b] && dst < D.bin_start[b + 1] && dst < D.capacity);
       D.rec_s[dst] = sm.rec[i];
     }
     __syncthreads();
@@ -387,6 +390,7 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
       {
         const unsigned long long v = (unsigned long long)chain::to_fixed(m, L);
         const int c = (gy - y0) * TW + gx - x0;
+        SLICER_CHECK(gx - x0 >= 1 && gx - x0 <= TILE && gy - y0 >= 1 && gy - y0 <= TILE);
         const unsigned vl = (unsigned)v, vh = (unsigned)(v >> 32);
         const unsigned old = atomicAdd(lo + c, vl);
         atomicAdd(hi + c, vh + ((old + vl < old) ? 1u : 0u));
@@ -423,6 +427,7 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
     {
       // interior stencil (all but the map's border): nine unconditional limb pairs, no branches — adding a zero
       // limb is harmless and cheaper than testing for it
+      SLICER_CHECK(lx >= 0 && lx + 2 < TW && ly >= 0 && ly + 2 < TW); // the record belongs to this tile (+ halo)
 #pragma unroll
       for (int jy = 0; jy < 3; jy++)
 #pragma unroll
@@ -442,6 +447,7 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
           const int cx = gx + jx - 1, cy = gy + jy - 1;
           if (cx < 0 || cx >= nn || cy < 0 || cy >= nn)
             continue; // utilities.cpp:91 drops cells outside the map
+          SLICER_CHECK(lx + jx >= 0 && lx + jx < TW && ly + jy >= 0 && ly + jy < TW);
           const unsigned long long v = (unsigned long long)chain::to_fixed(__fmul_rn(wx[jx], wy[jy]), L);
           const unsigned vl = (unsigned)v, vh = (unsigned)(v >> 32);
           const unsigned old = atomicAdd(plo + jy * TW + jx, vl);

@@ -8,6 +8,20 @@
 #include <stdint.h>
 #include "../../include/slicer_b200.h"
 
+// Device-side bounds checks of the checked build (`make checked` -> libslicer_b200_chk.so, loaded when SLICER_B200_LIB points
+// to it): a violated condition traps, the next API call then fails with the CUDA error.  compute-sanitizer is not always
+// available on shared GPU pools; these cover every computed index of the queues, record regions, sort and tiles.
+#ifdef SLICER_CHECKS
+#define SLICER_CHECK(cond) \
+  do                       \
+  {                        \
+    if (!(cond))           \
+      __trap();            \
+  } while (0)
+#else
+#define SLICER_CHECK(cond) ((void)0)
+#endif
+
 struct XformDev
 {
   double box;    // Header.boxsize (data.h:70)

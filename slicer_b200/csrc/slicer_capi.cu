@@ -859,6 +859,7 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
     Q.bin_start = h->bin.bin_start;
     Q.rec_s = h->bin.rec_s;
     Q.mass_s = D.mass ? h->bin.mass_s : nullptr;
+    Q.capacity = h->bin.capacity;
     if (pipelined_launch_emit(grid, P, S, E, h->compute))
       return fail("record kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     const int nwin = (nbins + binned::MAX_BINS - 1) / binned::MAX_BINS;

@@ -537,3 +537,18 @@ def test_seven_million_accepted_particles_bit_exact(oracle):
             assert res["counts"][1] > 6_000_000
         assert got["counts"].tolist() == res["counts"].tolist() and got["ingrid"].tolist() == res["ingrid"].tolist()
         assert np.array_equal(got["fixed"][1], res["fixed"][1])
+
+
+def test_checked_build_traps_nothing():
+    """The same tests against the build with device-side bounds checks (`make -C slicer_b200/csrc checked`, SLICER_CHECK in
+    csrc/pass_params.h: queue slots, record regions, sort slots and destinations, tile cells).  A violated check traps and the
+    test fails with the CUDA error.  Runs in a fresh interpreter because the library is loaded once per process."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    chk = os.path.join(root, "slicer_b200", "_build", "libslicer_b200_chk.so")
+    if not os.path.exists(chk):
+        pytest.skip("checked build not present (python -c 'import __graft_entry__ as g; g.build()')")
+    sel = "golden or ragged or binned or degradation or randomised or boundaries or clustered or multi_plane"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", sel, "-p", "no:cacheprovider"],
+                       env=dict(os.environ, SLICER_B200_LIB=chk), cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
