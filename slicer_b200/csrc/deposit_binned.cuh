@@ -485,6 +485,7 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
     if (v)
     {
       const int cy = y0 + i / TW, cx = x0 + i % TW;
+      SLICER_CHECK(cx >= 0 && cx < nn && cy >= 0 && cy < nn); // halo cells outside the map never receive mass
       chain::red_add(map + (size_t)cx + (size_t)nn * cy, (long long)v);
     }
   }

@@ -356,7 +356,8 @@ def test_large_scale_paths_agree():
                 assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2] and a[3] == b[3] and np.array_equal(a[4], b[4])
 
 
-def test_binned_deposit_bin_windows_for_huge_maps():
+@pytest.mark.parametrize("mas", [capi.MAS_TSC, capi.MAS_NGP])
+def test_binned_deposit_bin_windows_for_huge_maps(mas):
     """8192^2 maps: 2500 tiles per plane, so three planes exceed the 4096 bins one sort can hold: the records are produced
     once and sorted / deposited in two windows of 3750 bins (a window boundary inside a plane).  The result must equal
     the direct path's (int64 maps and counters)."""
@@ -368,7 +369,7 @@ def test_binned_deposit_bin_windows_for_huge_maps():
     descs = [capi.plane_desc([1, -1, 1], 2, [0.25, 0.5, 0.75], 1.0, 128.0 + 32.0 * k, 128.0 + 32.0 * (k + 1), fov, npix) for k in range(3)]
     out = {}
     for mode in (capi.DEPOSIT_DIRECT, capi.DEPOSIT_BINNED):
-        with capi.Slicer(npix_max=npix, max_planes=3, mas=capi.MAS_TSC, particle_capacity=n + 64, deposit_mode=mode) as s:
+        with capi.Slicer(npix_max=npix, max_planes=3, mas=mas, particle_capacity=n + 64, deposit_mode=mode) as s:
             s.begin_snapshot(box, [0, 1.5, 0, 0, 0, 0], False)
             s.stage(1, pos)
             s.deposit(descs)
