@@ -4,7 +4,8 @@
 // not fit the L2 (4 planes x 32 MiB at 2048^2) run at ~9 G particles/s — 20x below the particle stream.  This path
 // splits the pass into
 //   K1  deposit_pipelined_kernel<..., EMIT>  stream + screen + exact chain up to the map coordinates (xs, ys);
-//       every accepted particle becomes an 8-byte record, appended by its warp to a private region (no atomics)
+//       every accepted particle becomes an 8-byte record, appended to its CTA's region (one shared-memory atomic per warp
+//       and emit, no global atomics)
 //   K2a bin_histogram_kernel                 records per (region, bin); K2b/K2c scans -> offset of every region in
 //                                            every bin (no global atomics, deterministic bin layout)
 //   K2d bin_scatter_kernel                   counting sort of the records by (plane, map tile) bin
@@ -70,7 +71,7 @@ __device__ __forceinline__ int bin_of(int q, int gx, int gy, int nn, int ntile)
   return (q * ntile + cy) * ntile + cx;
 }
 
-// keys of a region, four at a time (region offsets are multiples of 128 records, so the 8-byte loads are aligned)
+// keys of a region, four at a time (region offsets are multiples of 1024 records, so the 8-byte loads are aligned)
 template <typename F>
 __device__ __forceinline__ void for_each_key(const unsigned short *key, unsigned n, int tid, int nthreads, F f)
 {

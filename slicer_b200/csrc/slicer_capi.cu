@@ -805,8 +805,8 @@ static int binned_alloc(slicer_handle *h)
     return 1;
   if (h->cfg.mass_capacity && (dev_alloc(h, &h->bin.mass_u, cap) || dev_alloc(h, &h->bin.mass_s, cap)))
     return 1;
-  if (dev_alloc(h, &h->bin.region_count, (size_t)h->pipe.grid_max * pipe::NCONS) ||
-      dev_alloc(h, &h->bin.region_hist, (size_t)binned::MAX_BINS * h->pipe.grid_max * pipe::NCONS) ||
+  if (dev_alloc(h, &h->bin.region_count, (size_t)h->pipe.grid_max) ||
+      dev_alloc(h, &h->bin.region_hist, (size_t)binned::MAX_BINS * h->pipe.grid_max) ||
       dev_alloc(h, &h->bin.bin_count, (size_t)binned::MAX_BINS) || dev_alloc(h, &h->bin.bin_start, (size_t)binned::MAX_BINS + 1))
     return 1;
   h->bin.slice = slice;
@@ -840,9 +840,9 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
     E.key = h->bin.key_u;
     E.mass = D.mass ? h->bin.mass_u : nullptr;
     E.region_count = h->bin.region_count;
-    E.region_cap = cmax * (pipe::CHUNK / pipe::NCONS);
+    E.region_cap = cmax * pipe::CHUNK; // one region per K1 CTA: every particle of its chunks could be accepted
     E.ntile = nt;
-    const int nregions = grid * pipe::NCONS;
+    const int nregions = grid;
     if ((unsigned long long)nregions * E.region_cap > h->bin.capacity)
       return fail("binned deposit: record buffer too small (internal error)");
     binned::SortDev Q;
