@@ -10,6 +10,8 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <memory>
+#include <thread>
 
 namespace slicer
 {
@@ -453,6 +455,20 @@ int runLightCone(const std::string &inifile, const RunOptions &opt)
 
   Engine *e = nullptr;
   int status = 0;
+  // The planes of a snapshot are written by a background thread while the next snapshot is read and deposited (an 8192^2
+  // plane is 256 MiB of byte-swapped FITS).  At most one snapshot's planes are in flight.
+  std::thread writer;
+  int writer_status = 0;
+  double writer_seconds = 0;
+  auto join_writer = [&]() {
+    if (writer.joinable())
+    {
+      writer.join();
+      t_write += writer_seconds;
+      if (writer_status)
+        status = 1;
+    }
+  };
   for (int s0 = 0; s0 < lens.nplanes && !status;)
   {
     // planes [s0, s1) use the same snapshot
@@ -501,32 +517,56 @@ int runLightCone(const std::string &inifile, const RunOptions &opt)
         status = 1;
         break;
       }
-      for (size_t j = 0; j < jobs.size(); j++)
+      join_writer(); // the previous snapshot's planes
+      if (status)
+        break;
+      struct Batch
       {
-        const int isnap = jobs[j].isnap;
-        const double zsim = cosmo.getZl.eval((lens.ld2[isnap] + lens.ld[isnap]) / 2.0);
-        InputParams pj = p;
-        pj.npix = jobs[j].npix;
+        std::vector<PlaneJob> jobs;
+        std::vector<double> zsim;
+        std::vector<std::valarray<float>> tot, per;
+        std::vector<long long> cnt;
+        Header snapdata;
+      };
+      auto batch = std::make_shared<Batch>();
+      batch->jobs = jobs;
+      for (size_t j = 0; j < jobs.size(); j++)
+        batch->zsim.push_back(cosmo.getZl.eval((lens.ld2[jobs[j].isnap] + lens.ld[jobs[j].isnap]) / 2.0));
+      batch->tot = std::move(tot);
+      batch->per = std::move(per);
+      batch->cnt = std::move(cnt);
+      batch->snapdata = snapdata;
+      writer_status = 0;
+      writer_seconds = 0;
+      writer = std::thread([batch, &p, &lens, &writer_status, &writer_seconds]() {
         const double tw0 = now_s();
-        try
+        for (size_t j = 0; j < batch->jobs.size(); j++)
         {
-          writeMaps(pj, snapdata, lens, isnap, zsim, plane_label(lens.pll[isnap]), tot[j], p.partinplanes ? &per[j * 6] : nullptr, &cnt[j * 6], 0);
-          t_write += now_s() - tw0;
+          const int isnap = batch->jobs[j].isnap;
+          InputParams pj = p;
+          pj.npix = batch->jobs[j].npix;
+          try
+          {
+            writeMaps(pj, batch->snapdata, lens, isnap, batch->zsim[j], plane_label(lens.pll[isnap]), batch->tot[j],
+                      p.partinplanes ? &batch->per[j * 6] : nullptr, &batch->cnt[j * 6], 0);
+          }
+          catch (const SliceError &err)
+          {
+            std::cerr << "It was not possible to create the map: " << err.what << std::endl;
+            writer_status = 1;
+            break;
+          }
         }
-        catch (const SliceError &err)
-        {
-          std::cerr << "It was not possible to create the map: " << err.what << std::endl;
-          status = 1;
-          break;
-        }
-      }
+        writer_seconds = now_s() - tw0;
+      });
     }
     s0 = s1;
   }
+  join_writer();
   engineDestroy(e);
   if (getenv("SLICER_B200_TIMING"))
     std::cerr << "[timing] total " << now_s() - t_begin << " s: engine/CUDA set-up " << t_engine << ", sub-file reads " << t_read << ", fetch (waits for the GPU) " << t_fetch
-              << ", FITS writes " << t_write << std::endl;
+              << ", FITS writes (background thread) " << t_write << std::endl;
   return status;
 }
 
