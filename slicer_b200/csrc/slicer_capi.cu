@@ -2,6 +2,7 @@
 // kernel launches, NCCL reduce.  Host-side arithmetic that feeds the kernel (minDist/maxDist, T, dl) is written
 // with the reference's own expressions so the doubles are bit-identical:
 //   densitymaps.cpp:346-347 (minDist,maxDist)  :383 (T)  utilities.cpp:50 (dl)  utilities.cpp:9,11 (0.5*dx, 0.5*3.0*dx)
+#include <chrono>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -246,10 +247,18 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
   memset(&h->stats, 0, sizeof(h->stats));
   memset(h->plane_npix, 0, sizeof(h->plane_npix));
   int rc = 0;
+  // SLICER_B200_TIMING: wall-clock of the set-up phases on stderr (context, allocations, kernel set-up)
+  const bool timing = getenv("SLICER_B200_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_start = now();
+  double t_ctx = 0, t_alloc = 0;
   do
   {
     if ((rc = set_device(h)))
       break;
+    if (timing)
+      cudaFree(nullptr); // force the context now, so that the phases are attributed correctly
+    t_ctx = now();
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess)
     {
@@ -304,6 +313,7 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
       break;
     if ((rc = dev_alloc(h, &h->d_sum, h->npix2max)))
       break;
+    t_alloc = now();
     if ((rc = pipelined_init(&h->pipe, h->sm_count)))
     {
       rc = fail("pipelined kernel set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -316,6 +326,9 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
       rc = fail("initial memset failed: %s", cudaGetErrorString(cudaGetLastError()));
       break;
     }
+    if (timing)
+      fprintf(stderr, "[timing] slicer_create(device %d): context %.3f s, streams + device allocations %.3f s, kernel set-up %.3f s\n", cfg->device,
+              t_ctx - t_start, t_alloc - t_ctx, now() - t_alloc);
   } while (0);
   if (rc)
   {
