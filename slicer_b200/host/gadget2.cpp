@@ -92,15 +92,18 @@ static int ensure_capacity(SubFile &s, size_t n, bool need_mass, bool pinned)
     if (slicer_alloc_pinned(cap * 3 * sizeof(float), &p))
       return 1;
     s.pos = (float *)p;
-    if (slicer_alloc_pinned(cap * sizeof(float), &m))
-      return 1;
-    s.mass = (float *)m;
+    if (need_mass)
+    {
+      if (slicer_alloc_pinned(cap * sizeof(float), &m))
+        return 1;
+      s.mass = (float *)m;
+    }
   }
   else
   {
     s.pos = (float *)malloc(cap * 3 * sizeof(float));
-    s.mass = (float *)malloc(cap * sizeof(float));
-    if (!s.pos || !s.mass)
+    s.mass = need_mass ? (float *)malloc(cap * sizeof(float)) : nullptr;
+    if (!s.pos || (need_mass && !s.mass))
       return 1;
   }
   s.capacity = cap;
@@ -199,7 +202,7 @@ int readSubFile(const std::string &file, bool hydro, SubFile &out, bool pinned)
     for (int i = 0; i < 6; i++)
       n += (size_t)h.npart[i];
     out.ntotal = n;
-    if (ensure_capacity(out, n, true, pinned))
+    if (ensure_capacity(out, n, hydro, pinned)) // the mass buffer only where per-particle masses can occur
     {
       std::cerr << "Out of (pinned) host memory for " << n << " particles\n";
       break;

@@ -141,7 +141,7 @@ extern "C"
       return 2;
     if (pos)
       memcpy(pos, s.pos, s.ntotal * 12);
-    if (mass)
+    if (mass && s.mass)
       memcpy(mass, s.mass, s.ntotal * 4);
     return 0;
   }
