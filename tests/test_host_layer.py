@@ -150,3 +150,16 @@ def test_reader_parallel_bulk_read(tmp_path):
     import zlib
     out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, SLICER_B200_IO_THREADS="1"), capture_output=True, text=True, check=True)
     assert out.stdout.split() == [str(zlib.crc32(s["pos"].tobytes())), str(zlib.crc32(s["mass"].tobytes()))]
+
+
+@pytest.mark.parametrize("n", [50_000, 1_200_000])  # plain fread path and the multi-threaded path (>= 8 MiB)
+def test_reader_rejects_truncated_pos_block(tmp_path, n):
+    """A sub-file cut off inside its POS payload is an error (the reference reads garbage silently; here: loud, rc != 0)."""
+    box = 100000.0
+    base = str(tmp_path / "snap_cut")
+    synth.write_snapshot(base, {1: synth.uniform_positions(n, box, 21)}, [0, 0.5, 0, 0, 0, 0], 0.1, box, numfiles=1, with_vel_id=False)
+    size = os.path.getsize(base + ".0")
+    with open(base + ".0", "r+b") as f:
+        f.truncate(size - n * 6)  # lose the second half of the positions
+    with pytest.raises(RuntimeError):
+        host.read_subfile(base + ".0", False, n + 10)
