@@ -794,7 +794,9 @@ static int use_binned(const slicer_handle *h, const PassParams &P, const Segment
     return 0; // record keys are 16 bits (16 planes of 10624^2 pixels still fit)
   if (h->cfg.deposit_mode == SLICER_DEPOSIT_BINNED)
     return 1;
-  if (D.n < (1ull << 22))
+  // the sort + tile kernels cost ~65 us per segment before the first record; a record then costs ~50 ps against ~105 ps of
+  // direct atomics (measured on 2^24- and 2^27-particle segments): worth it from ~1.2 million expected records
+  if (P.est_accept * (double)D.n < 1.2e6)
     return 0;
   // measured break-even: 3 % of the snapshot accepted; 1.5 % when one slice holds the whole batch, or when
   // the planes' accumulators are several times the L2 (> 256 MiB, e.g. 4096^2 and 8192^2 maps: the direct path's atomics go to HBM)
