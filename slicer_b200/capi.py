@@ -84,6 +84,7 @@ EXPORTS = [
     "slicer_reduce", "slicer_fetch", "slicer_fetch_fixed", "slicer_synchronize", "slicer_get_stats",
     "slicer_frac_bits", "slicer_comm_unique_id", "slicer_comm_init_rank", "slicer_comm_init_all",
     "slicer_reduce_all", "slicer_wait_staging", "slicer_count_accepted", "slicer_deposit_degraded", "slicer_reset_stats", "slicer_timer_begin", "slicer_timer_end",
+    "slicer_selftest_arith",
 ]
 
 
@@ -118,6 +119,7 @@ def lib() -> C.CDLL:
     L.slicer_next_batch.argtypes = [C.c_void_p]
     L.slicer_reset_stats.argtypes = [C.c_void_p]
     L.slicer_timer_begin.argtypes = [C.c_void_p]
+    L.slicer_selftest_arith.argtypes = [C.c_void_p, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
     L.slicer_timer_end.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.slicer_stage_particles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.slicer_stage_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
@@ -286,6 +288,12 @@ class Slicer:
         arr = planes if isinstance(planes, C.Array) else self._array(planes)
         fn = lib().slicer_deposit_accumulate if accumulate else lib().slicer_deposit
         _check(fn(self.h, arr, len(arr)))
+
+    def selftest_arith(self, n: int, seed: int):
+        """(division, square-root) results of the guard-free forms that differ from the IEEE library versions."""
+        out = (C.c_ulonglong * 2)()
+        _check(lib().slicer_selftest_arith(self.h, int(n), int(seed), out))
+        return tuple(int(v) for v in out)
 
     def count_accepted(self, planes: Sequence[PlaneDesc]) -> np.ndarray:
         """-> int64 [nplanes, 6]: accepted (particle, replica) pairs of the resident batch per plane and type."""

@@ -986,6 +986,24 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
   return 0;
 }
 
+extern "C" int slicer_selftest_arith(slicer_handle *h, unsigned long long n, unsigned long long seed, unsigned long long out[2])
+{
+  if (!h || !out)
+    return fail("null argument");
+  if (set_device(h))
+    return 1;
+  unsigned long long *d = (unsigned long long *)h->d_out; // npix_max^2 floats of scratch
+  if (h->npix2max * sizeof(float) < 2 * sizeof(unsigned long long))
+    return fail("slicer_selftest_arith needs npix_max >= 2");
+  CU(cudaStreamSynchronize(h->compute));
+  CU(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+  selftest_arith_kernel<<<h->sm_count * 8, 256, 0, h->compute>>>(n, seed, d);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(h->compute));
+  CU(cudaMemcpy(out, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 extern "C" int slicer_deposit(slicer_handle *h, const slicer_plane_desc *planes, int nplanes)
 {
   return run_pass(h, planes, nplanes, false);

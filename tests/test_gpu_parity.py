@@ -553,3 +553,12 @@ def test_checked_build_traps_nothing():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-m", "gpu", "-k", sel, "-p", "no:cacheprovider"],
                        env=dict(os.environ, SLICER_B200_LIB=chk), cwd=root, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_guard_free_arithmetic_equals_ieee_library(seed):
+    """The exact pair path uses guard-free forms of the IEEE double division and square root (csrc/device_chain.cuh): the
+    library's own fast paths without the range guard.  Bit-compare with __ddiv_rn / __dsqrt_rn on 1e9 random operand pairs
+    per seed, drawn from the exponent ranges an accepted particle can produce."""
+    with capi.Slicer(npix_max=64, max_planes=1, mas=capi.MAS_TSC, particle_capacity=1024) as s:
+        assert s.selftest_arith(1_000_000_000, 7919 * seed) == (0, 0)
