@@ -382,10 +382,13 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
   for (int i = threadIdx.x; i < 2 * TCELLS; i += DEPOSIT_THREADS)
     tile_smem[i] = 0;
   __syncthreads();
-  auto one = [&](float xs, float ys, float m) {
+  // `sm` = sqrtf(mass) (utilities.cpp:86-89 multiplies each 1-D weight by it); for a constant-mass segment it is hoisted out
+  // of the record loop (the IEEE square root is a guarded sequence of ~15 instructions)
+  const float sm_const = __fsqrt_rn(const_mass);
+  auto one = [&](float xs, float ys, float m, float sm) {
     const int gx = __float2int_rd(__fmul_rn(xs, L.npixf));
     const int gy = __float2int_rd(__fmul_rn(ys, L.npixf));
-    if (MAS == SLICER_MAS_NGP)
+    if constexpr (MAS == SLICER_MAS_NGP)
     { // utilities.cpp:72-76: the whole mass goes to the nearest grid point, if it is inside the map
       if (gx >= 0 && gx < nn && gy >= 0 && gy < nn)
       {
@@ -396,9 +399,9 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
         const unsigned old = atomicAdd(lo + c, vl);
         atomicAdd(hi + c, vh + ((old + vl < old) ? 1u : 0u));
       }
-      return;
     }
-    const float sm = __fsqrt_rn(m);
+    else
+    {
     float wx[3], wy[3];
 #pragma unroll
     for (int k = 0; k < 3; k++)
@@ -455,6 +458,7 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
           atomicAdd(phi + jy * TW + jx, vh + ((old + vl < old) ? 1u : 0u));
         }
     }
+    }
   };
   {
     unsigned i = r0 + threadIdx.x;
@@ -470,12 +474,13 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
       }
 #pragma unroll
       for (int j = 0; j < 4; j++)
-        one(e[j].x, e[j].y, m[j]);
+        one(e[j].x, e[j].y, m[j], D.mass_s ? __fsqrt_rn(m[j]) : sm_const);
     }
     for (; i < r1; i += DEPOSIT_THREADS)
     {
       const float2 e0 = D.rec_s[i];
-      one(e0.x, e0.y, D.mass_s ? D.mass_s[i] : const_mass);
+      const float m0 = D.mass_s ? D.mass_s[i] : const_mass;
+      one(e0.x, e0.y, m0, D.mass_s ? __fsqrt_rn(m0) : sm_const);
     }
   }
   __syncthreads();
