@@ -55,3 +55,14 @@ def test_no_cpu_fallback():
     with pytest.raises(capi.SlicerError) as e:
         capi.Slicer(npix_max=16)
     assert "CUDA" in str(e.value) or "cuda" in str(e.value)
+
+
+def test_plain_c_example_compiles_and_links(tmp_path):
+    """examples/minimal.c uses the ABI from C99 (no C++ or torch types in the signatures) and links against the library."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "minimal")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "minimal.c"),
+                        "-L" + os.path.join(root, "slicer_b200", "_build"), "-lslicer_b200", "-Wl,-rpath," + os.path.join(root, "slicer_b200", "_build"),
+                        "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
