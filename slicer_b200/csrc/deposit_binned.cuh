@@ -15,7 +15,9 @@
 //                                            32-bit limbs (carry from the returned old value), then flushed once
 //                                            with red.global.add.u64.
 // The int64 sums are exact and order independent, so the result is bit-identical to the direct path.
-// Requirements (PassParams::fast): power-of-two npix equal for all planes, no perpendicular replication.
+// K2/K3 sort and deposit at most MAX_BINS bins at a time: maps with more (plane, tile) bins (8192^2) are handled in windows
+// of the bin range over the SAME records (SortDev::bin_lo), i.e. K1 still runs once.
+// Requirements (PassParams::fast): power-of-two npix equal for all planes, no perpendicular replication, <= 65536 bins.
 #pragma once
 #include <cuda_runtime.h>
 #include "device_chain.cuh"
