@@ -44,6 +44,7 @@ class Config(C.Structure):
         ("staging_buffers", C.c_int),
         ("deposit_mode", C.c_int),
         ("record_capacity", C.c_size_t),
+        ("guard_eta", C.c_double),
     ]
 
 
@@ -74,6 +75,8 @@ class Stats(C.Structure):
         ("deposit_ms_sum", C.c_double),
         ("deposit_passes", C.c_ulonglong),
         ("deposit_launches", C.c_ulonglong),
+        ("flagged_pairs", C.c_ulonglong),
+        ("flagged_void", C.c_ulonglong),
     ]
 
 
@@ -201,11 +204,11 @@ class Slicer:
     def __init__(self, npix_max: int, max_planes: int = 4, mas: int = MAS_TSC, particle_capacity: int = 0,
                  mass_capacity: int = 0, per_type_maps: bool = False, device: int = 0, kernel: int = KERNEL_AUTO,
                  frac_bits: int = 0, max_m: float = 1e3, staging_buffers: int = 1, deposit_mode: int = DEPOSIT_AUTO,
-                 record_capacity: int = 0):
+                 record_capacity: int = 0, guard_eta: float = 0.0):
         cfg = Config(device=device, mas=mas, max_m=max_m, frac_bits=frac_bits, max_planes=max_planes,
                      npix_max=npix_max, per_type_maps=int(per_type_maps), particle_capacity=particle_capacity,
                      mass_capacity=mass_capacity, kernel=kernel, staging_buffers=staging_buffers, deposit_mode=deposit_mode,
-                     record_capacity=record_capacity)
+                     record_capacity=record_capacity, guard_eta=guard_eta)
         h = C.c_void_p()
         _check(lib().slicer_create(C.byref(cfg), C.byref(h)))
         self.h = h
@@ -290,8 +293,9 @@ class Slicer:
         _check(fn(self.h, arr, len(arr)))
 
     def selftest_arith(self, n: int, seed: int):
-        """(division, square-root) results of the guard-free forms that differ from the IEEE library versions."""
-        out = (C.c_ulonglong * 2)()
+        """(double division, double square root, float raw/box division of the lean box transform): how many results of the
+        guard-free forms differ from the IEEE library versions."""
+        out = (C.c_ulonglong * 3)()
         _check(lib().slicer_selftest_arith(self.h, int(n), int(seed), out))
         return tuple(int(v) for v in out)
 

@@ -101,3 +101,37 @@ __global__ void selftest_arith_kernel(unsigned long long n, unsigned long long s
   if (bad_sqrt)
     atomicAdd(out + 1, bad_sqrt);
 }
+
+// The unchecked float division of the lean box transform (deposit_pipelined.cuh: lean_div_box) against __fdiv_rn:
+// n random (raw coordinate, box size) pairs, box in [2^-40, 2^40), raw in [2^-40, box].  out[2] += quotients that differ.
+__device__ __forceinline__ float selftest_box_rcp(float boxf)
+{
+  const float y0 = lean_rcp_seed(boxf);
+  return __fmaf_rn(y0, __fmaf_rn(y0, -boxf, 1.0f), y0);
+}
+__global__ void selftest_fdiv_kernel(unsigned long long n, unsigned long long seed, unsigned long long *out)
+{
+  unsigned long long bad = 0;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+  {
+    const unsigned long long h1 = selftest_mix(seed + 2 * i), h2 = selftest_mix(seed + 2 * i + 1);
+    // a few boxes per warp iteration would hide nothing: every sample draws its own box (random mantissa and exponent)
+    const float b = __uint_as_float((unsigned)(h1 & 0x007fffffu) | ((unsigned)(127 - 40 + (h1 >> 32) % 80) << 23));
+    // raw = box * U(0,1] with a random mantissa, sometimes the box itself or a tiny value
+    float u = __uint_as_float((unsigned)(h2 & 0x007fffffu) | ((unsigned)(127 - 40 + (h2 >> 32) % 80) << 23));
+    if (u > b)
+      u = __fmul_rn(b, __uint_as_float((unsigned)(h2 & 0x007fffffu) | (126u << 23))); // b * [0.5, 1)
+    if ((h2 >> 60) == 0)
+      u = b;
+    if (!(u >= 0x1p-40f))
+      u = 0x1p-40f;
+    const float yb = selftest_box_rcp(b);
+    const float q0 = __fmul_rn(u, yb);
+    const float r = __fmaf_rn(q0, -b, u);
+    const float q = __fmaf_rn(yb, r, q0);
+    bad += __float_as_uint(q) != __float_as_uint(__fdiv_rn(u, b));
+  }
+  if (bad)
+    atomicAdd(out + 2, bad);
+}

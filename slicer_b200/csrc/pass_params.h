@@ -7,6 +7,7 @@
 #pragma once
 #include <stdint.h>
 #include "../../include/slicer_b200.h"
+#include "lean_math.h"
 
 // Device-side bounds checks of the checked build (`make checked` -> libslicer_b200_chk.so, loaded when SLICER_B200_LIB points
 // to it): a violated condition traps, the next API call then fails with the CUDA error.  compute-sanitizer is not always
@@ -45,6 +46,9 @@ struct XformDev
   float zlo_m, zhi_m; // zmin/zmax widened by the screen's error margin
   float zamb;       // z-wrap ambiguity: |w - 0.5| > zamb  => undecidable
   float raw_hi;     // raw coordinates outside the open interval (0, raw_hi) may wrap in the exact chain => undecidable
+  // --- fast box transform of the lean exact phase (deposit_pipelined.cuh: lean_axis), valid for raw in (LeanDev::umin, raw_hi) ---
+  float nboxf;      // -boxf: residual r = fma(q0, -box, u) of the division u / box
+  float wadd[3];    // 1 when sgn[k] < 0 (the wrap 1 + q of gadget2io.cpp:213-214 always fires), else 0 (no wrap can fire)
 };
 
 struct PlaneDev
@@ -82,8 +86,27 @@ struct PassParams
   int pair;  // fast, and all planes share one field (T, fovrad) with a small-angle series: two survivors per lane
   double est_accept; // host estimate of the accepted fraction of a uniform snapshot (chooses the deposit path)
   int debug; // measurement aid (env SLICER_B200_DEBUG): bit0 skip the map atomics, bit1 skip the exact chain; 0 in production
+  LeanDev lean; // lean projection + ambiguity guard (lean_math.h); enabled for `pair` passes
   XformDev xf[SLICER_MAX_XFORMS];
   PlaneDev pl[SLICER_MAX_PLANES];
+};
+
+// Particles whose accept decision or float map coordinates lie within the lean projection's error bound of a boundary: the
+// kernels append them here (exact box coordinates, mass, plane) and the host recomputes them with libm exactly as the reference
+// does (slicer_capi.cu: resolve_deferred) before any accumulator is read.
+struct DeferEntry
+{
+  float x, y, z, m;      // box coordinates after gadget2io.cpp:204-270 (exact floats), particle mass after the MAX_M cut
+  unsigned pass;         // which pass of the handle (host-side table of the plane parameters)
+  unsigned short plane;  // device plane slot within that pass
+  unsigned short type;   // particle type
+};
+struct DeferDev
+{
+  DeferEntry *buf;
+  unsigned *count;    // entries appended so far (may exceed cap: the excess is lost and the pass is reported as failed)
+  unsigned cap;
+  unsigned pass;
 };
 
 struct SegmentDev

@@ -128,6 +128,7 @@ struct slicer_handle
   int nbuf = 1, cur_buf = 0;
   int debug = 0;
   bool no_series = false; // env SLICER_B200_NO_SERIES: always use libdevice asin/atan2 (A/B checks)
+  bool no_lean = false;   // env SLICER_B200_NO_LEAN: general exact chain instead of the lean projection + guard (A/B checks)
   float *d_pos_pool = nullptr;  // nbuf * (particle_capacity * 3 + 64) floats
   float *d_mass_pool = nullptr; // nbuf * (mass_capacity + 64) floats
   float *d_pos = nullptr;  // current pool
@@ -149,6 +150,24 @@ struct slicer_handle
   ncclComm_t comm = nullptr;
   int nranks = 1, rank = 0;
   PipelinedScratch pipe;
+  // lean exact phase: particles it could not decide (lean_math.h), settled with the host's libm by resolve_deferred()
+  struct SavedPass
+  {
+    PassParams P;
+    unsigned long long epoch[SLICER_MAX_PLANES]; // zeroing count of the accumulator slot of device plane k when the pass was submitted
+  };
+  struct
+  {
+    DeferEntry *buf = nullptr;
+    unsigned *count = nullptr;
+    DeferEntry *host = nullptr; // pinned mirror
+    unsigned cap = 0;
+    std::vector<SavedPass> passes; // passes since the last resolve; DeferEntry::pass indexes it
+    bool failed = false;
+  } defer;
+  unsigned long long slot_epoch[SLICER_MAX_PLANES];
+  size_t pos_stride = 0, mass_stride = 0; // floats per staging pool (16-byte multiples)
+  size_t pcap = 0, mcap = 0;              // particles / masses a pool holds, padding of the segments included
   // particles per slice the binned path will use (before allocation: what it would allocate)
   size_t bin_slice_hint() const
   {
@@ -241,6 +260,7 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
     h->cfg.max_m = 1e3; /* densitymaps.h:21 */
   h->ntypes_alloc = cfg->per_type_maps ? SLICER_NTYPES : 1;
   h->no_series = getenv("SLICER_B200_NO_SERIES") != nullptr;
+  h->no_lean = getenv("SLICER_B200_NO_LEAN") != nullptr;
   if (const char *dbg = getenv("SLICER_B200_DEBUG"))
     h->debug = atoi(dbg);
   h->npix2max = (size_t)cfg->npix_max * (size_t)cfg->npix_max;
@@ -298,11 +318,26 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
     }
 #undef TRY
     h->nbuf = cfg->staging_buffers >= 2 ? 2 : 1;
-    // +64 floats of slack so 16-byte bulk copies may over-read the tail of the last chunk
-    if (cfg->particle_capacity && (rc = dev_alloc(h, &h->d_pos_pool, h->nbuf * (cfg->particle_capacity * 3 + 64))))
+    // +64 floats of slack so 16-byte bulk copies may over-read the tail of the last chunk; every pool starts on a 16-byte
+    // boundary whatever the capacity (cp.async.bulk needs 16-byte aligned sources)
+    // (internal capacities: the caller's, rounded up to a multiple of 4, plus room for the 16-byte padding of up to 8 segments)
+    h->pcap = cfg->particle_capacity ? ((cfg->particle_capacity + 3) & ~(size_t)3) + 32 : 0;
+    h->mcap = cfg->mass_capacity ? ((cfg->mass_capacity + 3) & ~(size_t)3) + 32 : 0;
+    h->pos_stride = h->pcap * 3 + 64;
+    h->mass_stride = h->mcap + 64;
+    if (cfg->particle_capacity && (rc = dev_alloc(h, &h->d_pos_pool, h->nbuf * h->pos_stride)))
       break;
-    if (cfg->mass_capacity && (rc = dev_alloc(h, &h->d_mass_pool, h->nbuf * (cfg->mass_capacity + 64))))
+    if (cfg->mass_capacity && (rc = dev_alloc(h, &h->d_mass_pool, h->nbuf * h->mass_stride)))
       break;
+    h->defer.cap = 1u << 20;
+    if ((rc = dev_alloc(h, &h->defer.buf, (size_t)h->defer.cap)) || (rc = dev_alloc(h, &h->defer.count, 1)))
+      break;
+    if (cudaHostAlloc((void **)&h->defer.host, (size_t)h->defer.cap * sizeof(DeferEntry), cudaHostAllocDefault) != cudaSuccess)
+    {
+      rc = fail("cudaHostAlloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    memset(h->slot_epoch, 0, sizeof(h->slot_epoch));
     h->d_pos = h->d_pos_pool;
     h->d_mass = h->d_mass_pool;
     if ((rc = dev_alloc(h, &h->d_acc, (size_t)cfg->max_planes * h->ntypes_alloc * h->npix2max)))
@@ -321,6 +356,7 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
     }
     if (cudaMemsetAsync(h->d_acc, 0, (size_t)cfg->max_planes * h->ntypes_alloc * h->npix2max * 8, h->compute) != cudaSuccess ||
         cudaMemsetAsync(h->d_counts, 0, (size_t)SLICER_MAX_PLANES * SLICER_NTYPES * 2 * 8, h->compute) != cudaSuccess ||
+        cudaMemsetAsync(h->defer.count, 0, sizeof(unsigned), h->compute) != cudaSuccess ||
         cudaStreamSynchronize(h->compute) != cudaSuccess)
     {
       rc = fail("initial memset failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -364,6 +400,10 @@ extern "C" void slicer_destroy(slicer_handle *h)
   cudaFree(h->bin.bin_count);
   cudaFree(h->bin.bin_start);
   cudaFree(h->bin.region_hist);
+  cudaFree(h->defer.buf);
+  cudaFree(h->defer.count);
+  if (h->defer.host)
+    cudaFreeHost(h->defer.host);
   cudaFree(h->d_pos_pool);
   cudaFree(h->d_mass_pool);
   cudaFree(h->d_acc);
@@ -420,8 +460,8 @@ extern "C" int slicer_next_batch(slicer_handle *h)
   h->cur_buf = (h->cur_buf + 1) % h->nbuf;
   // this pool is about to be overwritten: copies must wait for the pass that last read it
   CU(cudaStreamWaitEvent(h->copy, h->ev_buf_done[h->cur_buf], 0));
-  h->d_pos = h->d_pos_pool ? h->d_pos_pool + (size_t)h->cur_buf * (h->cfg.particle_capacity * 3 + 64) : nullptr;
-  h->d_mass = h->d_mass_pool ? h->d_mass_pool + (size_t)h->cur_buf * (h->cfg.mass_capacity + 64) : nullptr;
+  h->d_pos = h->d_pos_pool ? h->d_pos_pool + (size_t)h->cur_buf * h->pos_stride : nullptr;
+  h->d_mass = h->d_mass_pool ? h->d_mass_pool + (size_t)h->cur_buf * h->mass_stride : nullptr;
   h->segs.clear();
   h->pos_used = 0;
   h->mass_used = 0;
@@ -462,9 +502,9 @@ extern "C" int slicer_stage_particles(slicer_handle *h, int type, const float *p
   if (pm && !mass)
     return fail("slicer_stage_particles: type %d has massarr==0 in a hydro snapshot: per-particle masses required", type);
   const size_t npad = pad4(n);
-  if (h->pos_used + npad > h->cfg.particle_capacity)
+  if (h->pos_used + npad > h->pcap)
     return fail("slicer_stage_particles: %zu particles exceed particle_capacity %zu", h->pos_used + n, h->cfg.particle_capacity);
-  if (pm && h->mass_used + npad > h->cfg.mass_capacity)
+  if (pm && h->mass_used + npad > h->mcap)
     return fail("slicer_stage_particles: %zu masses exceed mass_capacity %zu", h->mass_used + n, h->cfg.mass_capacity);
   Segment s;
   s.type = type;
@@ -527,7 +567,7 @@ extern "C" int slicer_stage_synthetic(slicer_handle *h, int type, size_t n, uint
   if (uses_particle_mass(h, type))
     return fail("slicer_stage_synthetic: synthetic segments carry no per-particle mass");
   const size_t npad = pad4(n);
-  if (h->pos_used + npad > h->cfg.particle_capacity)
+  if (h->pos_used + npad > h->pcap)
     return fail("slicer_stage_synthetic: %zu particles exceed particle_capacity %zu", h->pos_used + n, h->cfg.particle_capacity);
   Segment s;
   s.type = type;
@@ -752,6 +792,9 @@ static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int npl
     X.zamb = 0.5f - 2e-6f;
     X.thr_m = isinf(X.tmax) ? 0.f : 4e-6f + X.tmax * mz * 1.01f;
     X.raw_hi = float_floor(h->boxsize * (1.0 - 1e-6)); // 0 < raw < raw_hi  =>  raw/box in (0,1): no wrap at the first site
+    X.nboxf = -X.boxf;
+    for (int k = 0; k < 3; k++)
+      X.wadd[k] = X.sgn[k] < 0.f ? 1.f : 0.f;
   }
   P->pair = P->fast && P->pl[0].nt > 0;
   for (int t = 0; t < P->nxform; t++)
@@ -760,6 +803,19 @@ static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int npl
   for (int q = 1; q < P->nplanes; q++)
     if (P->pl[q].T != P->pl[0].T || P->pl[q].fovrad != P->pl[0].fovrad || P->pl[q].npix != P->pl[0].npix)
       P->pair = 0;
+  // lean exact phase (lean_math.h, deposit_pipelined.cuh: drain_lean): one narrow field and map size for all planes, float-exact
+  // box and centres, and a box size for which the unchecked float division cannot leave the normal range
+  P->lean.enabled = 0;
+  if (P->pair && h->boxsize >= 0x1p-40 && h->boxsize <= 0x1p40 && !h->no_lean)
+  {
+    lean_setup(&P->lean, P->pl[0].fovrad, P->pl[0].T, h->cfg.guard_eta);
+    if (!(P->xf[0].raw_hi > P->lean.umin))
+      P->lean.enabled = 0;
+    for (int t = 0; t < P->nxform; t++)
+      for (int k = 0; k < 3; k++)
+        if (!(P->xf[t].cf[k] >= 0.f && P->xf[t].cf[k] <= 1.f))
+          P->lean.enabled = 0; // lean_axis assumes a centre inside the box (randomizeBox draws it in [0, 1])
+  }
   return 0;
 }
 
@@ -804,8 +860,13 @@ static int use_binned(const slicer_handle *h, const PassParams &P, const Segment
   return P.est_accept > (h->bin_slice_hint() >= D.n || big_maps ? 0.015 : 0.03) ? 1 : 0;
 }
 
-static int binned_alloc(slicer_handle *h)
+static int binned_alloc(slicer_handle *h, bool need_mass)
 {
+  if (h->bin.rec_u && need_mass && !h->bin.mass_u)
+  { // first segment with per-particle masses on this handle (e.g. staged from device memory without a mass_capacity)
+    if (dev_alloc(h, &h->bin.mass_u, h->bin.capacity) || dev_alloc(h, &h->bin.mass_s, h->bin.capacity))
+      return 1;
+  }
   if (h->bin.rec_u)
     return 0;
   size_t slice = h->cfg.record_capacity ? h->cfg.record_capacity : ((size_t)1 << 28);
@@ -815,10 +876,11 @@ static int binned_alloc(slicer_handle *h)
   if (slice > cap_particles)
     slice = cap_particles;
   slice = (slice + pipe::CHUNK - 1) / pipe::CHUNK * pipe::CHUNK;
-  const size_t cap = slice + (size_t)h->pipe.grid_max * pipe::CHUNK; // every warp region is rounded up to whole chunks
+  // every CTA region is rounded up to whole chunks, times the randomisations of a pass (one record per particle and randomisation)
+  const size_t cap = slice + ((size_t)h->pipe.grid_max + 1) * pipe::CHUNK * SLICER_MAX_XFORMS;
   if (dev_alloc(h, &h->bin.rec_u, cap) || dev_alloc(h, &h->bin.rec_s, cap) || dev_alloc(h, &h->bin.key_u, cap))
     return 1;
-  if (h->cfg.mass_capacity && (dev_alloc(h, &h->bin.mass_u, cap) || dev_alloc(h, &h->bin.mass_s, cap)))
+  if ((h->cfg.mass_capacity || need_mass) && (dev_alloc(h, &h->bin.mass_u, cap) || dev_alloc(h, &h->bin.mass_s, cap)))
     return 1;
   if (dev_alloc(h, &h->bin.region_count, (size_t)h->pipe.grid_max) ||
       dev_alloc(h, &h->bin.region_hist, (size_t)binned::MAX_BINS * h->pipe.grid_max) ||
@@ -829,9 +891,9 @@ static int binned_alloc(slicer_handle *h)
   return 0;
 }
 
-static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &D)
+static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &D, const DeferDev &F)
 {
-  if (binned_alloc(h))
+  if (binned_alloc(h, D.mass != nullptr))
     return 1;
   const int nt = binned_tiles(P);
   const int nbins = P.nplanes * nt * nt;
@@ -841,6 +903,13 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
   // (not for maps of several bin windows: their tiles are sparsely filled, the per-tile zero + flush dominates)
   if (P.est_accept >= 0.12 && nbins <= binned::MAX_BINS && slice > ((size_t)1 << 28))
     slice = (size_t)1 << 28;
+  // a particle yields up to one record per randomisation of the pass: the slice shrinks so that the regions still fit
+  if (P.nxform > 1)
+  {
+    slice = slice / P.nxform / pipe::CHUNK * pipe::CHUNK;
+    if (slice < (size_t)pipe::CHUNK)
+      slice = pipe::CHUNK;
+  }
   for (unsigned long long off = 0; off < D.n; off += slice)
   {
     SegmentDev S = D;
@@ -855,7 +924,7 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
     E.key = h->bin.key_u;
     E.mass = D.mass ? h->bin.mass_u : nullptr;
     E.region_count = h->bin.region_count;
-    E.region_cap = cmax * pipe::CHUNK; // one region per K1 CTA: every particle of its chunks could be accepted
+    E.region_cap = cmax * pipe::CHUNK * (unsigned long long)P.nxform; // one region per K1 CTA: every (particle, randomisation) pair of its chunks could be accepted
     E.ntile = nt;
     const int nregions = grid;
     if ((unsigned long long)nregions * E.region_cap > h->bin.capacity)
@@ -875,7 +944,7 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
     Q.rec_s = h->bin.rec_s;
     Q.mass_s = D.mass ? h->bin.mass_s : nullptr;
     Q.capacity = h->bin.capacity;
-    if (pipelined_launch_emit(grid, P, S, E, h->compute))
+    if (pipelined_launch_emit(grid, P, S, E, F, h->compute))
       return fail("record kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     const int nwin = (nbins + binned::MAX_BINS - 1) / binned::MAX_BINS;
     const int wbins = (nbins + nwin - 1) / nwin;
@@ -921,6 +990,124 @@ static int resolve_passes(slicer_handle *h, size_t n)
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// deferred particles of the lean exact phase (lean_math.h): the reference's own arithmetic with this host's libm
+// ------------------------------------------------------------------------------------------------------------
+struct ResolvedRec
+{
+  float xs, ys, m;
+  unsigned short plane, type;
+};
+static_assert(sizeof(ResolvedRec) <= sizeof(DeferEntry), "resolved records are uploaded into the deferred buffer");
+
+template <int MAS>
+__global__ void resolved_deposit_kernel(const __grid_constant__ PassParams P, const ResolvedRec *__restrict__ r, unsigned n)
+{
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const ResolvedRec e = r[i];
+  const PlaneDev &L = P.pl[e.plane];
+  atomicAdd(L.counts + 2 * e.type, 1ull);
+  if (P.debug & 1)
+    return;
+  if (chain::deposit<MAS>(e.xs, e.ys, e.m, L, L.acc + L.type_stride * (unsigned long long)e.type))
+    atomicAdd(L.counts + 2 * e.type + 1, 1ull);
+}
+
+// densitymaps.cpp:382-386 + utilities.cpp:23-25 for one particle (ni = nj = 0), evaluated on the host like the reference
+// (same libm; this translation unit is compiled without FMA contraction)
+static bool host_project(const DeferEntry &e, const PlaneDev &L, float *xs, float *ys)
+{
+  volatile double X = (double)e.x - 0.5, Y = (double)e.y - 0.5, Z = (double)e.z;
+  volatile double xx = X * X, yy = Y * Y, zz = Z * Z;
+  volatile double sum = xx + yy;
+  sum = sum + zz;
+  const double d = sqrt(sum);
+  volatile double sd = X / d;
+  const double dec = asin(sd);
+  const double ra = atan2(Y, Z);
+  if (!(fabs(ra) <= L.T && fabs(dec) <= L.T))
+    return false;
+  volatile double vx = dec / L.fovrad, vy = ra / L.fovrad;
+  vx = vx + 0.5;
+  vy = vy + 0.5;
+  *xs = (float)vx;
+  *ys = (float)vy;
+  return true;
+}
+
+// Settle every particle the lean exact phase deferred since the last call.  Blocks until the passes submitted so far are done.
+static int resolve_deferred(slicer_handle *h)
+{
+  if (h->defer.passes.empty())
+    return 0;
+  if (set_device(h))
+    return 1;
+  unsigned n = 0;
+  CU(cudaMemcpyAsync(&n, h->defer.count, sizeof(unsigned), cudaMemcpyDeviceToHost, h->compute));
+  CU(cudaStreamSynchronize(h->compute));
+  if (n > h->defer.cap)
+  {
+    h->defer.failed = true;
+    h->defer.passes.clear();
+    CU(cudaMemsetAsync(h->defer.count, 0, sizeof(unsigned), h->compute));
+    return fail("%u particles within the rounding guard of a decision boundary exceed the deferred buffer (%u): the planes deposited since the "
+                "last fetch are incomplete; deposit and fetch in smaller batches",
+                n, h->defer.cap);
+  }
+  if (n)
+  {
+    CU(cudaMemcpyAsync(h->defer.host, h->defer.buf, (size_t)n * sizeof(DeferEntry), cudaMemcpyDeviceToHost, h->compute));
+    CU(cudaStreamSynchronize(h->compute));
+    const size_t np = h->defer.passes.size();
+    std::vector<std::vector<ResolvedRec>> out(np);
+    for (unsigned i = 0; i < n; i++)
+    {
+      const DeferEntry &e = h->defer.host[i];
+      if (e.pass >= np || e.plane >= SLICER_MAX_PLANES)
+        return fail("corrupt deferred entry (internal error)");
+      const slicer_handle::SavedPass &sp = h->defer.passes[e.pass];
+      const PlaneDev &L = sp.P.pl[e.plane];
+      if (sp.epoch[e.plane] != h->slot_epoch[L.slot])
+      {
+        h->stats.flagged_void++;
+        continue; // the accumulator was zeroed after that pass
+      }
+      ResolvedRec r;
+      h->stats.flagged_pairs++;
+      if (!host_project(e, L, &r.xs, &r.ys))
+        continue;
+      r.m = e.m;
+      r.plane = e.plane;
+      r.type = e.type;
+      out[e.pass].push_back(r);
+    }
+    ResolvedRec *dev = reinterpret_cast<ResolvedRec *>(h->defer.buf);
+    ResolvedRec *stage = reinterpret_cast<ResolvedRec *>(h->defer.host);
+    size_t off = 0;
+    for (size_t k = 0; k < np; k++)
+    {
+      const unsigned m = (unsigned)out[k].size();
+      if (!m)
+        continue;
+      memcpy(stage + off, out[k].data(), (size_t)m * sizeof(ResolvedRec));
+      CU(cudaMemcpyAsync(dev + off, stage + off, (size_t)m * sizeof(ResolvedRec), cudaMemcpyHostToDevice, h->compute));
+      if (h->cfg.mas == SLICER_MAS_NGP)
+        resolved_deposit_kernel<SLICER_MAS_NGP><<<(m + 127) / 128, 128, 0, h->compute>>>(h->defer.passes[k].P, dev + off, m);
+      else
+        resolved_deposit_kernel<SLICER_MAS_TSC><<<(m + 127) / 128, 128, 0, h->compute>>>(h->defer.passes[k].P, dev + off, m);
+      CU(cudaGetLastError());
+      h->stats.launches++;
+      off += m;
+    }
+    CU(cudaMemsetAsync(h->defer.count, 0, sizeof(unsigned), h->compute));
+    CU(cudaStreamSynchronize(h->compute)); // the pinned mirror is reused by the next call
+  }
+  h->defer.passes.clear();
+  return 0;
+}
+
 static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplanes, bool accumulate)
 {
   if (!h || !planes)
@@ -936,10 +1123,27 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
     CU(cudaStreamWaitEvent(h->compute, h->ev_copy, 0));
     h->copy_pending = false;
   }
+  if (h->defer.passes.size() >= 4096 && resolve_deferred(h))
+    return 1;
   if (!accumulate)
   {
     CU(cudaMemsetAsync(h->d_acc, 0, (size_t)nplanes * h->ntypes_alloc * h->npix2max * sizeof(unsigned long long), h->compute));
     CU(cudaMemsetAsync(h->d_counts, 0, (size_t)nplanes * SLICER_NTYPES * 2 * sizeof(unsigned long long), h->compute));
+    for (int q = 0; q < nplanes; q++)
+      h->slot_epoch[q]++; // deferred particles of earlier passes into these accumulators are void
+  }
+  DeferDev F;
+  F.buf = h->defer.buf;
+  F.count = h->defer.count;
+  F.cap = h->defer.cap;
+  F.pass = (unsigned)h->defer.passes.size();
+  if (P.lean.enabled)
+  {
+    slicer_handle::SavedPass sp;
+    sp.P = P;
+    for (int k = 0; k < P.nplanes; k++)
+      sp.epoch[k] = h->slot_epoch[P.pl[k].slot];
+    h->defer.passes.push_back(sp);
   }
   int kernel = h->cfg.kernel;
   if (kernel == SLICER_KERNEL_AUTO)
@@ -959,10 +1163,10 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
       const int ub = use_binned(h, P, D);
       if (ub == 1)
       {
-        if (binned_pass(h, P, D))
+        if (binned_pass(h, P, D, F))
           return 1;
       }
-      else if (pipelined_launch(&h->pipe, h->cfg.mas, P, D, h->compute))
+      else if (pipelined_launch(&h->pipe, h->cfg.mas, P, D, F, h->compute))
         return fail("pipelined launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     else
@@ -986,21 +1190,22 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
   return 0;
 }
 
-extern "C" int slicer_selftest_arith(slicer_handle *h, unsigned long long n, unsigned long long seed, unsigned long long out[2])
+extern "C" int slicer_selftest_arith(slicer_handle *h, unsigned long long n, unsigned long long seed, unsigned long long out[3])
 {
   if (!h || !out)
     return fail("null argument");
   if (set_device(h))
     return 1;
   unsigned long long *d = (unsigned long long *)h->d_out; // npix_max^2 floats of scratch
-  if (h->npix2max * sizeof(float) < 2 * sizeof(unsigned long long))
-    return fail("slicer_selftest_arith needs npix_max >= 2");
+  if (h->npix2max * sizeof(float) < 3 * sizeof(unsigned long long))
+    return fail("slicer_selftest_arith needs npix_max >= 3");
   CU(cudaStreamSynchronize(h->compute));
-  CU(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+  CU(cudaMemset(d, 0, 3 * sizeof(unsigned long long)));
   selftest_arith_kernel<<<h->sm_count * 8, 256, 0, h->compute>>>(n, seed, d);
+  selftest_fdiv_kernel<<<h->sm_count * 8, 256, 0, h->compute>>>(n, seed, d);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->compute));
-  CU(cudaMemcpy(out, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(out, d, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -1148,6 +1353,8 @@ extern "C" int slicer_deposit_degraded(slicer_handle *h, const slicer_plane_desc
   {
     CU(cudaMemsetAsync(h->d_acc, 0, (size_t)nplanes * h->ntypes_alloc * h->npix2max * sizeof(unsigned long long), h->compute));
     CU(cudaMemsetAsync(h->d_counts, 0, (size_t)nplanes * SLICER_NTYPES * 2 * sizeof(unsigned long long), h->compute));
+    for (int q = 0; q < nplanes; q++)
+      h->slot_epoch[q]++;
   }
   if (total == 0)
     return 0;
@@ -1210,6 +1417,8 @@ extern "C" int slicer_synchronize(slicer_handle *h)
   if (set_device(h))
     return 1;
   CU(cudaStreamSynchronize(h->copy));
+  if (resolve_deferred(h))
+    return 1;
   CU(cudaStreamSynchronize(h->compute));
   return 0;
 }
@@ -1245,7 +1454,7 @@ static int check_plane(slicer_handle *h, int plane, int type)
 extern "C" int slicer_fetch(slicer_handle *h, int plane, int type, float *out_map, long long counts[SLICER_NTYPES],
                             long long ingrid[SLICER_NTYPES])
 {
-  if (check_plane(h, plane, type))
+  if (check_plane(h, plane, type) || resolve_deferred(h))
     return 1;
   const size_t npix2 = (size_t)h->plane_npix[plane] * h->plane_npix[plane];
   const unsigned long long *base = h->d_acc + (size_t)plane * h->ntypes_alloc * h->npix2max;
@@ -1274,7 +1483,7 @@ extern "C" int slicer_fetch(slicer_handle *h, int plane, int type, float *out_ma
 
 extern "C" int slicer_fetch_fixed(slicer_handle *h, int plane, int type, long long *out)
 {
-  if (check_plane(h, plane, type))
+  if (check_plane(h, plane, type) || resolve_deferred(h))
     return 1;
   if (!out)
     return fail("slicer_fetch_fixed: null output");
@@ -1402,10 +1611,18 @@ extern "C" int slicer_comm_init_all(slicer_handle **handles, int n)
   return 0;
 }
 
+// one ncclReduce per (plane, type) accumulator over the npix^2 cells that plane uses (not the npix_max^2 it is allocated with)
 static int enqueue_reduce(slicer_handle *h, int nplanes, int root)
 {
-  const size_t count = (size_t)nplanes * h->ntypes_alloc * h->npix2max;
-  NC(g_nccl.Reduce(h->d_acc, h->d_acc, count, ncclInt64, ncclSum, root, h->comm, h->compute));
+  for (int q = 0; q < nplanes; q++)
+  {
+    const size_t npix2 = h->plane_npix[q] > 0 ? (size_t)h->plane_npix[q] * h->plane_npix[q] : h->npix2max;
+    for (int t = 0; t < h->ntypes_alloc; t++)
+    {
+      unsigned long long *a = h->d_acc + ((size_t)q * h->ntypes_alloc + t) * h->npix2max;
+      NC(g_nccl.Reduce(a, a, npix2, ncclInt64, ncclSum, root, h->comm, h->compute));
+    }
+  }
   NC(g_nccl.Reduce(h->d_counts, h->d_counts, (size_t)nplanes * SLICER_NTYPES * 2, ncclUint64, ncclSum, root, h->comm, h->compute));
   return 0;
 }
@@ -1418,12 +1635,16 @@ extern "C" int slicer_reduce(slicer_handle *h, int nplanes, int root)
     return 0;
   if (nplanes < 1 || nplanes > h->cfg.max_planes)
     return fail("slicer_reduce: nplanes %d outside 1..%d", nplanes, h->cfg.max_planes);
-  if (set_device(h))
+  if (set_device(h) || resolve_deferred(h))
     return 1;
   NC(g_nccl.GroupStart());
-  int rc = enqueue_reduce(h, nplanes, root);
-  NC(g_nccl.GroupEnd());
-  return rc;
+  const int rc = enqueue_reduce(h, nplanes, root);
+  const ncclResult_t ge = g_nccl.GroupEnd(); // always closes the group, also when a reduce could not be enqueued
+  if (rc)
+    return rc;
+  if (ge != ncclSuccess)
+    return fail("ncclGroupEnd failed: %s", g_nccl.GetErrorString(ge));
+  return 0;
 }
 
 extern "C" int slicer_reduce_all(slicer_handle **handles, int n, int nplanes, int root)
@@ -1434,6 +1655,9 @@ extern "C" int slicer_reduce_all(slicer_handle **handles, int n, int nplanes, in
     return 0;
   if (load_nccl())
     return 1;
+  for (int i = 0; i < n; i++)
+    if (!handles[i] || resolve_deferred(handles[i]))
+      return 1;
   NC(g_nccl.GroupStart());
   int rc = 0;
   for (int i = 0; i < n && !rc; i++)
@@ -1443,6 +1667,10 @@ extern "C" int slicer_reduce_all(slicer_handle **handles, int n, int nplanes, in
     else
       rc = enqueue_reduce(handles[i], nplanes, root);
   }
-  NC(g_nccl.GroupEnd());
-  return rc;
+  const ncclResult_t ge = g_nccl.GroupEnd();
+  if (rc)
+    return rc;
+  if (ge != ncclSuccess)
+    return fail("ncclGroupEnd failed: %s", g_nccl.GetErrorString(ge));
+  return 0;
 }

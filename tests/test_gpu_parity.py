@@ -557,8 +557,155 @@ def test_checked_build_traps_nothing():
 
 @pytest.mark.parametrize("seed", [1, 2, 3, 4])
 def test_guard_free_arithmetic_equals_ieee_library(seed):
-    """The exact pair path uses guard-free forms of the IEEE double division and square root (csrc/device_chain.cuh): the
-    library's own fast paths without the range guard.  Bit-compare with __ddiv_rn / __dsqrt_rn on 1e9 random operand pairs
-    per seed, drawn from the exponent ranges an accepted particle can produce."""
+    """The exact phase uses guard-free forms of IEEE operations: the library's own fast paths without the range guard
+    (csrc/device_chain.cuh: ddiv_fast, dsqrt_fast; csrc/deposit_pipelined.cuh: lean_div_box = the float division raw / box of
+    gadget2io.cpp:204-206).  Bit-compare with __ddiv_rn / __dsqrt_rn / __fdiv_rn on 1e9 random operand pairs per seed, drawn
+    from the exponent ranges the paths admit."""
     with capi.Slicer(npix_max=64, max_planes=1, mas=capi.MAS_TSC, particle_capacity=1024) as s:
-        assert s.selftest_arith(1_000_000_000, 7919 * seed) == (0, 0)
+        assert s.selftest_arith(1_000_000_000, 7919 * seed) == (0, 0, 0)
+
+
+@pytest.mark.parametrize("mas", [capi.MAS_TSC, capi.MAS_NGP])
+@pytest.mark.parametrize("mode", [capi.DEPOSIT_DIRECT, capi.DEPOSIT_BINNED])
+def test_rounding_guard_sends_ambiguous_pairs_to_libm(oracle, mas, mode):
+    """The lean projection (csrc/lean_math.h) is proven to within 2^-49.9 of the reference's double; whatever lies within the
+    guard of a decision boundary (field edge, float rounding of xs / ys) is recomputed with the host's libm like the reference
+    (utilities.cpp:23-25, densitymaps.cpp:383-386).  With the default guard (2^-47) that is a few pairs per million; widened to
+    2^-34 it is several per cent, which exercises the deferred path at volume: counts and int64 maps must still equal the
+    oracle's bit for bit, and the library must report how many pairs went that way."""
+    box = 128000.0
+    n = 1 << 21
+    pos = synth.uniform_positions(n, box, 11)
+    types = [dict(type=1, raw=pos, const_mass=1.0375)]
+    plane = dict(boxsize=box, sgn=[-1, 1, -1], face=5, centre=[0.75, 0.125, 0.5], rcase=1.0, ld=128.0 + 16, ld2=256.0, nrepperp=0,
+                 fovradiants=0.55)
+    npix = 512
+    res = None
+    flagged = {}
+    for eta in (0.0, 2.0 ** -34):
+        with capi.Slicer(npix_max=npix, max_planes=1, mas=mas, particle_capacity=n + 64, deposit_mode=mode, guard_eta=eta) as s:
+            s.begin_snapshot(box, [0, 1.0375, 0, 0, 0, 0], False)
+            s.stage(1, pos)
+            d = capi.plane_desc(plane["sgn"], plane["face"], plane["centre"], plane["rcase"], plane["ld"], plane["ld2"], plane["fovradiants"], npix)
+            s.deposit([d])
+            s.deposit([d], accumulate=True)  # twice: deferred pairs of both passes are settled together
+            fixed = s.fetch_fixed(0, -1, npix).reshape(-1)
+            _, counts, ingrid = s.fetch(0, -1, npix, want_map=False)
+            flagged[eta] = int(s.stats().flagged_pairs)
+            fb = s.frac_bits
+        if res is None:
+            res = oracle.plane_from_particles(types, plane, npix, do_ngp=mas == capi.MAS_NGP, frac_bits=fb)
+            assert res["counts"][1] > 1_000_000
+        assert counts.tolist() == (2 * res["counts"]).tolist() and ingrid.tolist() == (2 * res["ingrid"]).tolist()
+        assert np.array_equal(fixed, 2 * res["fixed"][1])
+    assert flagged[2.0 ** -34] > 20_000            # ~ 2 * 1.5e6 pairs * 2 coordinates * 2^-34 / 2^-24 per binade ...
+    assert flagged[0.0] < flagged[2.0 ** -34] // 1000  # ... and 2^13 times fewer with the production guard
+
+
+def test_deferred_pairs_of_a_zeroed_plane_are_dropped(oracle):
+    """A plain slicer_deposit zeroes the accumulators: pairs still waiting for the libm path from an earlier pass into the same
+    planes must not be added afterwards."""
+    box = 128000.0
+    n = 1 << 19
+    pos = synth.uniform_positions(n, box, 12)
+    types = [dict(type=1, raw=pos, const_mass=1.0)]
+    plane = dict(boxsize=box, sgn=[1, 1, 1], face=1, centre=[0.5, 0.5, 0.25], rcase=0.0, ld=32.0, ld2=128.0, nrepperp=0, fovradiants=0.5)
+    npix = 256
+    with capi.Slicer(npix_max=npix, max_planes=1, mas=capi.MAS_TSC, particle_capacity=n + 64, guard_eta=2.0 ** -32) as s:
+        s.begin_snapshot(box, [0, 1.0, 0, 0, 0, 0], False)
+        s.stage(1, pos)
+        d = capi.plane_desc(plane["sgn"], plane["face"], plane["centre"], plane["rcase"], plane["ld"], plane["ld2"], plane["fovradiants"], npix)
+        s.deposit([d])
+        s.deposit([d])  # starts over: the first pass's deferred pairs are void
+        fixed = s.fetch_fixed(0, -1, npix).reshape(-1)
+        _, counts, _ = s.fetch(0, -1, npix, want_map=False)
+        st = s.stats()
+        res = oracle.plane_from_particles(types, plane, npix, frac_bits=s.frac_bits)
+    assert counts.tolist() == res["counts"].tolist()
+    assert np.array_equal(fixed, res["fixed"][1])
+    assert st.flagged_void > 100 and st.flagged_pairs > 100
+
+
+def test_binned_dense_pass_with_two_randomisations(oracle):
+    """Two randomisations whose planes together accept most of the snapshot, in ONE binned pass: a particle then yields up to two
+    records, so a K1 CTA emits more records than it streams particles (the record regions must be sized for that)."""
+    box = 128000.0
+    n = 600000
+    pos = synth.uniform_positions(n, box, 21)
+    types = [dict(type=1, raw=pos, const_mass=1.0375)]
+    rnd = oracle.randomize_box(-229, -230, -231, [1, 1])
+    fov = 0.7  # wide enough that each plane takes ~80 % of the box in the lateral directions at z ~ 1.3 .. 2
+    npix = 256
+    planes = []
+    for i in range(2):
+        planes.append(dict(boxsize=box, sgn=[rnd["sgnX"][i], rnd["sgnY"][i], rnd["sgnZ"][i]], face=rnd["face"][i],
+                           centre=[rnd["x0"][i], rnd["y0"][i], rnd["z0"][i]], rcase=1.0, ld=128.0, ld2=256.0, nrepperp=0, fovradiants=fov))
+    descs = [capi.plane_desc(p["sgn"], p["face"], p["centre"], p["rcase"], p["ld"], p["ld2"], fov, npix) for p in planes]
+    for cap in (0, 65536):
+        with capi.Slicer(npix_max=npix, max_planes=2, mas=capi.MAS_TSC, particle_capacity=n + 64, deposit_mode=capi.DEPOSIT_BINNED,
+                         record_capacity=cap) as s:
+            s.begin_snapshot(box, [0, 1.0375, 0, 0, 0, 0], False)
+            s.stage(1, pos)
+            s.deposit(descs)
+            fb = s.frac_bits
+            total = 0
+            for k, p in enumerate(planes):
+                res = oracle.plane_from_particles(types, p, npix, frac_bits=fb)
+                _, counts, _ = s.fetch(k, -1, npix, want_map=False)
+                assert counts.tolist() == res["counts"].tolist()
+                assert np.array_equal(s.fetch_fixed(k, -1, npix).reshape(-1), res["fixed"][1])
+                total += int(counts[1])
+            assert total > n  # more records than particles
+
+
+@pytest.mark.parametrize("capacity", [100001, 100002, 100003])
+def test_two_staging_pools_with_any_capacity(oracle, capacity):
+    """Capacities that are not multiples of 4: the second staging pool must still start 16-byte aligned for the
+    TMA bulk copies, and a batch of exactly `capacity` particles must fit."""
+    box = 128000.0
+    pos = synth.uniform_positions(capacity, box, 31)
+    types = [dict(type=1, raw=pos, const_mass=1.0)]
+    plane = dict(boxsize=box, sgn=[1, 1, -1], face=2, centre=[0.5, 0.25, 0.5], rcase=0.0, ld=32.0, ld2=120.0, nrepperp=0, fovradiants=0.4)
+    npix = 128
+    d = capi.plane_desc(plane["sgn"], plane["face"], plane["centre"], plane["rcase"], plane["ld"], plane["ld2"], plane["fovradiants"], npix)
+    with capi.Slicer(npix_max=npix, max_planes=1, mas=capi.MAS_TSC, particle_capacity=capacity, staging_buffers=2) as s:
+        s.begin_snapshot(box, [0, 1.0, 0, 0, 0, 0], False)  # switches to pool 1
+        s.stage(1, pos)
+        s.deposit([d])
+        s.next_batch()                                       # pool 0
+        s.stage(1, pos)
+        s.deposit([d], accumulate=True)
+        fixed = s.fetch_fixed(0, -1, npix).reshape(-1)
+        res = oracle.plane_from_particles(types, plane, npix, frac_bits=s.frac_bits)
+    assert np.array_equal(fixed, 2 * res["fixed"][1])
+
+
+def test_binned_per_particle_mass_without_mass_capacity(oracle):
+    """Hydro segment staged from DEVICE memory on a handle created with mass_capacity == 0: the binned path must
+    carry the per-particle masses (it used to deposit float(massarr) = 0)."""
+    torch = pytest.importorskip("torch")
+    box = 128000.0
+    n = 400000
+    pos = synth.uniform_positions(n, box, 41)
+    rng = np.random.default_rng(5)
+    mass = (rng.random(n, dtype=np.float32) * 3 + 0.01).astype(np.float32)
+    mass[::97] = 2000.0  # above MAX_M: counted, deposited as 0
+    types = [dict(type=0, raw=pos, masses=mass)]
+    plane = dict(boxsize=box, sgn=[1, -1, 1], face=4, centre=[0.5, 0.5, 0.5], rcase=0.0, ld=20.0, ld2=127.0, nrepperp=0, fovradiants=0.6)
+    npix = 256
+    d = capi.plane_desc(plane["sgn"], plane["face"], plane["centre"], plane["rcase"], plane["ld"], plane["ld2"], plane["fovradiants"], npix)
+    dpos = torch.from_numpy(pos).cuda()
+    dmass = torch.from_numpy(mass).cuda()
+    torch.cuda.synchronize()
+    out = {}
+    for mode in (capi.DEPOSIT_DIRECT, capi.DEPOSIT_BINNED):
+        with capi.Slicer(npix_max=npix, max_planes=1, mas=capi.MAS_TSC, particle_capacity=0, mass_capacity=0, deposit_mode=mode) as s:
+            s.begin_snapshot(box, [0, 0, 0, 0, 0, 0], True)
+            s.stage_device(0, dpos.data_ptr(), n, dmass.data_ptr())
+            s.deposit([d])
+            out[mode] = s.fetch_fixed(0, -1, npix).reshape(-1)
+            fb = s.frac_bits
+    res = oracle.plane_from_particles(types, plane, npix, frac_bits=fb)
+    assert out[capi.DEPOSIT_BINNED].sum() > 0
+    assert np.array_equal(out[capi.DEPOSIT_DIRECT], out[capi.DEPOSIT_BINNED])
+    assert np.array_equal(out[capi.DEPOSIT_BINNED], res["fixed"][0])

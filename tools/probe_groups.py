@@ -23,4 +23,4 @@ for g in [int(v) for v in os.environ.get('PGROUPS', ','.join(str(i) for i in ran
     acc = sum(int(s.fetch(k, -1, NPIX, want_map=False)[1][1]) for k in range(4))
     print(f"group {g}: {st.last_deposit_ms:8.3f} ms  accepted {acc:11d} ({acc / n * 100:5.2f} %)  "
           f"{n / st.last_deposit_ms / 1e6:7.1f} Gpart/s  {12 * n / st.last_deposit_ms / 1e6 / 6551.7 * 100:5.1f} % roofline  "
-          f"{acc / st.last_deposit_ms / 1e6:6.2f} Grec/s", flush=True)
+          f"{acc / st.last_deposit_ms / 1e6:6.2f} Grec/s  flagged {st.flagged_pairs}+{st.flagged_void}", flush=True)
