@@ -369,11 +369,14 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
     tile_deposit_kernel(const __grid_constant__ PassParams P, const __grid_constant__ SortDev D, int ntile, int type, float const_mass)
 {
   extern __shared__ __align__(16) unsigned tile_smem[];
+  __shared__ unsigned s_ingrid;
   unsigned *lo = tile_smem;
   unsigned *hi = tile_smem + TCELLS;
   const unsigned r0 = D.bin_start[blockIdx.x], r1 = D.bin_start[blockIdx.x + 1];
   if (r0 == r1)
     return;
+  if (threadIdx.x == 0)
+    s_ingrid = 0;
   const int b = blockIdx.x + D.bin_lo;
   const int q = b / (ntile * ntile);
   const int tb = b - q * ntile * ntile;
@@ -381,6 +384,11 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
   const PlaneDev &L = P.pl[q];
   const int nn = L.npix;
   const int x0 = tx * TILE - 1, y0 = ty * TILE - 1; // map cell of local (0,0)
+  // The records of this bin are the accepted pairs of (plane, tile): this kernel keeps mapParticles' counters for the binned
+  // path (densitymaps.cpp:402-403), the record kernel does not count.  Only a border tile can hold records whose nearest
+  // grid point is outside the map.
+  const bool border = tx == 0 || ty == 0 || tx == ntile - 1 || ty == ntile - 1;
+  unsigned my_ingrid = 0;
   for (int i = threadIdx.x; i < 2 * TCELLS; i += DEPOSIT_THREADS)
     tile_smem[i] = 0;
   __syncthreads();
@@ -390,6 +398,8 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
   auto one = [&](float xs, float ys, float m, float sm) {
     const int gx = __float2int_rd(__fmul_rn(xs, L.npixf));
     const int gy = __float2int_rd(__fmul_rn(ys, L.npixf));
+    if (border)
+      my_ingrid += (gx >= 0 && gx < nn && gy >= 0 && gy < nn) ? 1u : 0u;
     if constexpr (MAS == SLICER_MAS_NGP)
     { // utilities.cpp:72-76: the whole mass goes to the nearest grid point, if it is inside the map
       if (gx >= 0 && gx < nn && gy >= 0 && gy < nn)
@@ -485,7 +495,18 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
       one(e0.x, e0.y, m0, D.mass_s ? __fsqrt_rn(m0) : sm_const);
     }
   }
+  if (border)
+  {
+    const unsigned wsum = __reduce_add_sync(0xffffffffu, my_ingrid);
+    if ((threadIdx.x & 31) == 0 && wsum)
+      atomicAdd(&s_ingrid, wsum);
+  }
   __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    atomicAdd(L.counts + 2 * type, (unsigned long long)(r1 - r0));
+    atomicAdd(L.counts + 2 * type + 1, (unsigned long long)(border ? s_ingrid : r1 - r0));
+  }
   unsigned long long *map = L.acc + L.type_stride * (unsigned long long)type;
   for (int i = threadIdx.x; i < TCELLS; i += DEPOSIT_THREADS)
   {
