@@ -87,7 +87,8 @@ EXPORTS = [
     "slicer_reduce", "slicer_fetch", "slicer_fetch_fixed", "slicer_synchronize", "slicer_get_stats",
     "slicer_frac_bits", "slicer_comm_unique_id", "slicer_comm_init_rank", "slicer_comm_init_all",
     "slicer_reduce_all", "slicer_wait_staging", "slicer_count_accepted", "slicer_deposit_degraded", "slicer_reset_stats", "slicer_timer_begin", "slicer_timer_end",
-    "slicer_selftest_arith",
+    "slicer_selftest_arith", "slicer_deposit_slots", "slicer_reduce_slots", "slicer_reduce_all_slots",
+    "slicer_stage_synthetic_window",
 ]
 
 
@@ -127,10 +128,14 @@ def lib() -> C.CDLL:
     L.slicer_stage_particles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.slicer_stage_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     L.slicer_stage_synthetic.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_uint64, C.c_int]
+    L.slicer_stage_synthetic_window.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong, C.c_size_t, C.c_uint64, C.c_int]
     L.slicer_download_segment.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.slicer_deposit.argtypes = [C.c_void_p, C.POINTER(PlaneDesc), C.c_int]
     L.slicer_deposit_accumulate.argtypes = [C.c_void_p, C.POINTER(PlaneDesc), C.c_int]
     L.slicer_reduce.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.slicer_deposit_slots.argtypes = [C.c_void_p, C.POINTER(PlaneDesc), C.c_int, C.c_int, C.c_int]
+    L.slicer_reduce_slots.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.slicer_reduce_all_slots.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]
     L.slicer_count_accepted.argtypes = [C.c_void_p, C.POINTER(PlaneDesc), C.c_int, C.c_void_p]
     L.slicer_deposit_degraded.argtypes = [C.c_void_p, C.POINTER(PlaneDesc), C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int]
     L.slicer_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -270,8 +275,8 @@ class Slicer:
         _check(lib().slicer_stage_device(self.h, int(ptype), C.c_void_p(dev_pos_ptr), int(layout),
                                          C.c_void_p(dev_mass_ptr) if dev_mass_ptr else None, int(n)))
 
-    def stage_synthetic(self, ptype: int, n: int, seed: int, layout: int = LAYOUT_AOS):
-        _check(lib().slicer_stage_synthetic(self.h, int(ptype), int(n), int(seed), int(layout)))
+    def stage_synthetic(self, ptype: int, n: int, seed: int, layout: int = LAYOUT_AOS, start: int = 0):
+        _check(lib().slicer_stage_synthetic_window(self.h, int(ptype), int(start), int(n), int(seed), int(layout)))
 
     def download_segment(self, segment: int, n: int, layout: int = LAYOUT_AOS, with_mass: bool = False):
         pos = np.empty((n, 3) if layout == LAYOUT_AOS else (3, n), np.float32)
@@ -291,6 +296,13 @@ class Slicer:
         arr = planes if isinstance(planes, C.Array) else self._array(planes)
         fn = lib().slicer_deposit_accumulate if accumulate else lib().slicer_deposit
         _check(fn(self.h, arr, len(arr)))
+
+    def deposit_slots(self, planes: Sequence[PlaneDesc], first_slot: int, accumulate: bool = False):
+        arr = planes if isinstance(planes, C.Array) else self._array(planes)
+        _check(lib().slicer_deposit_slots(self.h, arr, len(arr), int(first_slot), int(accumulate)))
+
+    def reduce_slots(self, first_slot: int, nplanes: int, root: int = 0):
+        _check(lib().slicer_reduce_slots(self.h, int(first_slot), int(nplanes), int(root)))
 
     def selftest_arith(self, n: int, seed: int):
         """(double division, double square root, float raw/box division of the lean box transform): how many results of the

@@ -42,8 +42,9 @@ __host__ __device__ inline uint64_t synth_mix(uint64_t seed, uint64_t idx)
   return z ^ (z >> 31);
 }
 
+// `start`: index of the segment's first particle in the realisation (a shard is a window of one realisation)
 __global__ void synth_positions_kernel(float *__restrict__ pos, unsigned long long n, unsigned long long soa_stride,
-                                       int layout_soa, uint64_t seed, float boxf)
+                                       int layout_soa, uint64_t seed, float boxf, unsigned long long start)
 {
   const unsigned long long total = 3ull * n;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -60,7 +61,7 @@ __global__ void synth_positions_kernel(float *__restrict__ pos, unsigned long lo
       i = j / 3ull;
       k = j - 3ull * i;
     }
-    const float u = (float)(synth_mix(seed, 3ull * i + k) >> 40) * (1.0f / 16777216.0f);
+    const float u = (float)(synth_mix(seed, 3ull * (start + i) + k) >> 40) * (1.0f / 16777216.0f);
     const float v = __fmul_rn(u, boxf);
     if (layout_soa)
       pos[k * soa_stride + i] = v;

@@ -119,7 +119,10 @@ struct slicer_handle
   int ntypes_alloc;
   size_t npix2max;
   int sm_count;
-  cudaStream_t compute = nullptr, copy = nullptr;
+  cudaStream_t compute = nullptr, copy = nullptr, comm_stream = nullptr;
+  cudaEvent_t ev_pass_done = nullptr;              // compute -> comm_stream: the passes a reduce sums
+  cudaEvent_t ev_slot[SLICER_MAX_PLANES];          // comm_stream -> compute: the last reduce of accumulator slot q
+  bool slot_reducing[SLICER_MAX_PLANES];           // ev_slot[q] is pending
   cudaEvent_t ev_copy = nullptr;
   cudaEvent_t ev_buf_done[2] = {nullptr, nullptr}; // last pass that read staging pool b
   cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;    // slicer_timer_*
@@ -249,6 +252,11 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
   if (cfg->device < 0 || cfg->device >= ndev)
     return fail("slicer_create: device %d out of range (have %d)", cfg->device, ndev);
   slicer_handle *h = new slicer_handle;
+  for (int q = 0; q < SLICER_MAX_PLANES; q++)
+  {
+    h->ev_slot[q] = nullptr;
+    h->slot_reducing[q] = false;
+  }
   h->cfg = *cfg;
   h->frac_bits = cfg->frac_bits > 0 ? cfg->frac_bits : 40;
   if (h->frac_bits > 60)
@@ -300,6 +308,10 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
   }
     TRY(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
     TRY(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
+    TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    TRY(cudaEventCreateWithFlags(&h->ev_pass_done, cudaEventDisableTiming));
+    for (int q = 0; q < SLICER_MAX_PLANES; q++)
+      TRY(cudaEventCreateWithFlags(&h->ev_slot[q], cudaEventDisableTiming));
     TRY(cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming));
     TRY(cudaEventCreateWithFlags(&h->ev_buf_done[0], cudaEventDisableTiming));
     TRY(cudaEventCreateWithFlags(&h->ev_buf_done[1], cudaEventDisableTiming));
@@ -384,6 +396,8 @@ extern "C" void slicer_destroy(slicer_handle *h)
     cudaStreamSynchronize(h->compute);
   if (h->copy)
     cudaStreamSynchronize(h->copy);
+  if (h->comm_stream)
+    cudaStreamSynchronize(h->comm_stream);
   if (h->comm && g_nccl.CommDestroy)
     g_nccl.CommDestroy(h->comm);
   pipelined_destroy(&h->pipe);
@@ -422,10 +436,17 @@ extern "C" void slicer_destroy(slicer_handle *h)
   for (size_t i = 0; i < h->pass_ev.size(); i++)
     if (h->pass_ev[i])
       cudaEventDestroy(h->pass_ev[i]);
+  if (h->ev_pass_done)
+    cudaEventDestroy(h->ev_pass_done);
+  for (int q = 0; q < SLICER_MAX_PLANES; q++)
+    if (h->ev_slot[q])
+      cudaEventDestroy(h->ev_slot[q]);
   if (h->compute)
     cudaStreamDestroy(h->compute);
   if (h->copy)
     cudaStreamDestroy(h->copy);
+  if (h->comm_stream)
+    cudaStreamDestroy(h->comm_stream);
   delete h;
 }
 
@@ -560,6 +581,11 @@ extern "C" int slicer_stage_device(slicer_handle *h, int type, const void *dev_p
 
 extern "C" int slicer_stage_synthetic(slicer_handle *h, int type, size_t n, uint64_t seed, int layout)
 {
+  return slicer_stage_synthetic_window(h, type, 0, n, seed, layout);
+}
+
+extern "C" int slicer_stage_synthetic_window(slicer_handle *h, int type, unsigned long long start, size_t n, uint64_t seed, int layout)
+{
   if (check_stage(h, type, layout))
     return 1;
   if (n == 0)
@@ -579,7 +605,7 @@ extern "C" int slicer_stage_synthetic(slicer_handle *h, int type, size_t n, uint
   s.dmass = nullptr;
   const int blocks = (int)((3 * n + 255) / 256 < (size_t)h->sm_count * 16 ? (3 * n + 255) / 256 : (size_t)h->sm_count * 16);
   // generated on the copy stream so it orders with other staging work
-  synth_positions_kernel<<<blocks, 256, 0, h->copy>>>(dst, n, npad, layout == SLICER_LAYOUT_SOA, seed, (float)h->boxsize);
+  synth_positions_kernel<<<blocks, 256, 0, h->copy>>>(dst, n, npad, layout == SLICER_LAYOUT_SOA, seed, (float)h->boxsize, start);
   CU(cudaGetLastError());
   h->stats.launches++;
   h->pos_used += npad;
@@ -1108,14 +1134,33 @@ static int resolve_deferred(slicer_handle *h)
   return 0;
 }
 
-static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplanes, bool accumulate)
+// compute-stream work on accumulator slots [lo, lo + n) must follow the reduces still running on them
+static int wait_slot_reduces(slicer_handle *h, int lo, int n)
+{
+  for (int q = lo; q < lo + n && q < SLICER_MAX_PLANES; q++)
+    if (h->slot_reducing[q])
+    {
+      CU(cudaStreamWaitEvent(h->compute, h->ev_slot[q], 0));
+      h->slot_reducing[q] = false;
+    }
+  return 0;
+}
+
+static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplanes, bool accumulate, int first_slot = 0)
 {
   if (!h || !planes)
     return fail("slicer_deposit: null argument");
   if (set_device(h))
     return 1;
+  if (first_slot < 0 || nplanes < 1 || first_slot + nplanes > h->cfg.max_planes)
+    return fail("slicer_deposit: slots %d..%d outside 0..%d (max_planes)", first_slot, first_slot + nplanes - 1, h->cfg.max_planes - 1);
+  int slot_of[SLICER_MAX_PLANES];
+  for (int i = 0; i < nplanes; i++)
+    slot_of[i] = first_slot + i;
   PassParams P;
-  if (build_pass(h, planes, nplanes, &P))
+  if (build_pass(h, planes, nplanes, &P, slot_of))
+    return 1;
+  if (wait_slot_reduces(h, first_slot, nplanes))
     return 1;
   if (h->copy_pending)
   {
@@ -1127,9 +1172,11 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
     return 1;
   if (!accumulate)
   {
-    CU(cudaMemsetAsync(h->d_acc, 0, (size_t)nplanes * h->ntypes_alloc * h->npix2max * sizeof(unsigned long long), h->compute));
-    CU(cudaMemsetAsync(h->d_counts, 0, (size_t)nplanes * SLICER_NTYPES * 2 * sizeof(unsigned long long), h->compute));
-    for (int q = 0; q < nplanes; q++)
+    CU(cudaMemsetAsync(h->d_acc + (size_t)first_slot * h->ntypes_alloc * h->npix2max, 0,
+                       (size_t)nplanes * h->ntypes_alloc * h->npix2max * sizeof(unsigned long long), h->compute));
+    CU(cudaMemsetAsync(h->d_counts + (size_t)first_slot * SLICER_NTYPES * 2, 0, (size_t)nplanes * SLICER_NTYPES * 2 * sizeof(unsigned long long),
+                       h->compute));
+    for (int q = first_slot; q < first_slot + nplanes; q++)
       h->slot_epoch[q]++; // deferred particles of earlier passes into these accumulators are void
   }
   DeferDev F;
@@ -1217,6 +1264,11 @@ extern "C" int slicer_deposit(slicer_handle *h, const slicer_plane_desc *planes,
 extern "C" int slicer_deposit_accumulate(slicer_handle *h, const slicer_plane_desc *planes, int nplanes)
 {
   return run_pass(h, planes, nplanes, true);
+}
+
+extern "C" int slicer_deposit_slots(slicer_handle *h, const slicer_plane_desc *planes, int nplanes, int first_slot, int accumulate)
+{
+  return run_pass(h, planes, nplanes, accumulate != 0, first_slot);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1420,6 +1472,7 @@ extern "C" int slicer_synchronize(slicer_handle *h)
   if (resolve_deferred(h))
     return 1;
   CU(cudaStreamSynchronize(h->compute));
+  CU(cudaStreamSynchronize(h->comm_stream));
   return 0;
 }
 
@@ -1454,7 +1507,7 @@ static int check_plane(slicer_handle *h, int plane, int type)
 extern "C" int slicer_fetch(slicer_handle *h, int plane, int type, float *out_map, long long counts[SLICER_NTYPES],
                             long long ingrid[SLICER_NTYPES])
 {
-  if (check_plane(h, plane, type) || resolve_deferred(h))
+  if (check_plane(h, plane, type) || resolve_deferred(h) || wait_slot_reduces(h, plane, 1))
     return 1;
   const size_t npix2 = (size_t)h->plane_npix[plane] * h->plane_npix[plane];
   const unsigned long long *base = h->d_acc + (size_t)plane * h->ntypes_alloc * h->npix2max;
@@ -1483,7 +1536,7 @@ extern "C" int slicer_fetch(slicer_handle *h, int plane, int type, float *out_ma
 
 extern "C" int slicer_fetch_fixed(slicer_handle *h, int plane, int type, long long *out)
 {
-  if (check_plane(h, plane, type) || resolve_deferred(h))
+  if (check_plane(h, plane, type) || resolve_deferred(h) || wait_slot_reduces(h, plane, 1))
     return 1;
   if (!out)
     return fail("slicer_fetch_fixed: null output");
@@ -1611,52 +1664,86 @@ extern "C" int slicer_comm_init_all(slicer_handle **handles, int n)
   return 0;
 }
 
-// one ncclReduce per (plane, type) accumulator over the npix^2 cells that plane uses (not the npix_max^2 it is allocated with)
-static int enqueue_reduce(slicer_handle *h, int nplanes, int root)
+// one ncclReduce per (plane, type) accumulator over the npix^2 cells that plane uses (not the npix_max^2 it is allocated with),
+// on the handle's communication stream: passes into OTHER accumulator slots keep running on the compute stream meanwhile
+static int enqueue_reduce(slicer_handle *h, int first_slot, int nplanes, int root)
 {
-  for (int q = 0; q < nplanes; q++)
+  for (int q = first_slot; q < first_slot + nplanes; q++)
   {
     const size_t npix2 = h->plane_npix[q] > 0 ? (size_t)h->plane_npix[q] * h->plane_npix[q] : h->npix2max;
     for (int t = 0; t < h->ntypes_alloc; t++)
     {
       unsigned long long *a = h->d_acc + ((size_t)q * h->ntypes_alloc + t) * h->npix2max;
-      NC(g_nccl.Reduce(a, a, npix2, ncclInt64, ncclSum, root, h->comm, h->compute));
+      NC(g_nccl.Reduce(a, a, npix2, ncclInt64, ncclSum, root, h->comm, h->comm_stream));
     }
   }
-  NC(g_nccl.Reduce(h->d_counts, h->d_counts, (size_t)nplanes * SLICER_NTYPES * 2, ncclUint64, ncclSum, root, h->comm, h->compute));
+  unsigned long long *c = h->d_counts + (size_t)first_slot * SLICER_NTYPES * 2;
+  NC(g_nccl.Reduce(c, c, (size_t)nplanes * SLICER_NTYPES * 2, ncclUint64, ncclSum, root, h->comm, h->comm_stream));
   return 0;
 }
 
-extern "C" int slicer_reduce(slicer_handle *h, int nplanes, int root)
+// order the reduce after the passes submitted so far, and everything that touches these slots later after the reduce
+static int reduce_fence_before(slicer_handle *h, int first_slot, int nplanes)
+{
+  if (wait_slot_reduces(h, first_slot, nplanes)) // an earlier reduce of the same slots (same stream anyway)
+    return 1;
+  CU(cudaEventRecord(h->ev_pass_done, h->compute));
+  CU(cudaStreamWaitEvent(h->comm_stream, h->ev_pass_done, 0));
+  return 0;
+}
+static int reduce_fence_after(slicer_handle *h, int first_slot, int nplanes)
+{
+  for (int q = first_slot; q < first_slot + nplanes; q++)
+  {
+    CU(cudaEventRecord(h->ev_slot[q], h->comm_stream));
+    h->slot_reducing[q] = true;
+  }
+  return 0;
+}
+
+extern "C" int slicer_reduce_slots(slicer_handle *h, int first_slot, int nplanes, int root)
 {
   if (!h)
     return fail("null handle");
-  if (!h->comm || h->nranks == 1)
-    return 0;
-  if (nplanes < 1 || nplanes > h->cfg.max_planes)
-    return fail("slicer_reduce: nplanes %d outside 1..%d", nplanes, h->cfg.max_planes);
+  if (nplanes < 1 || first_slot < 0 || first_slot + nplanes > h->cfg.max_planes)
+    return fail("slicer_reduce: slots %d..%d outside 0..%d", first_slot, first_slot + nplanes - 1, h->cfg.max_planes - 1);
   if (set_device(h) || resolve_deferred(h))
     return 1;
+  if (!h->comm || h->nranks == 1)
+    return 0;
+  if (reduce_fence_before(h, first_slot, nplanes))
+    return 1;
   NC(g_nccl.GroupStart());
-  const int rc = enqueue_reduce(h, nplanes, root);
+  const int rc = enqueue_reduce(h, first_slot, nplanes, root);
   const ncclResult_t ge = g_nccl.GroupEnd(); // always closes the group, also when a reduce could not be enqueued
   if (rc)
     return rc;
   if (ge != ncclSuccess)
     return fail("ncclGroupEnd failed: %s", g_nccl.GetErrorString(ge));
-  return 0;
+  return reduce_fence_after(h, first_slot, nplanes);
 }
 
-extern "C" int slicer_reduce_all(slicer_handle **handles, int n, int nplanes, int root)
+extern "C" int slicer_reduce(slicer_handle *h, int nplanes, int root) { return slicer_reduce_slots(h, 0, nplanes, root); }
+
+extern "C" int slicer_reduce_all_slots(slicer_handle **handles, int n, int first_slot, int nplanes, int root)
 {
   if (!handles || n < 1)
     return fail("slicer_reduce_all: bad arguments");
+  for (int i = 0; i < n; i++)
+  {
+    if (!handles[i])
+      return fail("slicer_reduce_all: null handle");
+    if (nplanes < 1 || first_slot < 0 || first_slot + nplanes > handles[i]->cfg.max_planes)
+      return fail("slicer_reduce_all: slots %d..%d outside 0..%d", first_slot, first_slot + nplanes - 1, handles[i]->cfg.max_planes - 1);
+    if (set_device(handles[i]) || resolve_deferred(handles[i]))
+      return 1;
+  }
   if (n == 1)
     return 0;
   if (load_nccl())
     return 1;
   for (int i = 0; i < n; i++)
-    if (!handles[i] || resolve_deferred(handles[i]))
+    if (set_device(handles[i]) || reduce_fence_before(handles[i], first_slot, nplanes))
       return 1;
   NC(g_nccl.GroupStart());
   int rc = 0;
@@ -1665,12 +1752,20 @@ extern "C" int slicer_reduce_all(slicer_handle **handles, int n, int nplanes, in
     if (cudaSetDevice(handles[i]->cfg.device) != cudaSuccess)
       rc = fail("cudaSetDevice failed");
     else
-      rc = enqueue_reduce(handles[i], nplanes, root);
+      rc = enqueue_reduce(handles[i], first_slot, nplanes, root);
   }
   const ncclResult_t ge = g_nccl.GroupEnd();
   if (rc)
     return rc;
   if (ge != ncclSuccess)
     return fail("ncclGroupEnd failed: %s", g_nccl.GetErrorString(ge));
+  for (int i = 0; i < n; i++)
+    if (set_device(handles[i]) || reduce_fence_after(handles[i], first_slot, nplanes))
+      return 1;
   return 0;
+}
+
+extern "C" int slicer_reduce_all(slicer_handle **handles, int n, int nplanes, int root)
+{
+  return slicer_reduce_all_slots(handles, n, 0, nplanes, root);
 }

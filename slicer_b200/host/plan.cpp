@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <iterator>
+#include <functional>
 #include <iostream>
 #include <limits>
 
@@ -21,113 +23,159 @@ static std::string sconv_int(int v)
   return b;
 }
 
-// data.cpp:8-87 — 14 values on the even lines of a positional file; odd lines are labels and ignored
+// ---------------------------------------------------------------------------------------------------------------
+// InputParams.ini (format of data.cpp:8-87): a positional file of 14 entries, each a label line followed by a value line.
+// The parse is table driven: entry k of the table says where value k goes and how it is converted; zs, fov and w go
+// through float precision because the reference parses them with stof (data.cpp:26,29,83).
+// ---------------------------------------------------------------------------------------------------------------
+namespace
+{
+enum class Conv { Int, Float, Flag, Text };
+struct IniEntry
+{
+  const char *what;
+  Conv conv;
+  void (*store)(InputParams &, const std::string &, long, float);
+};
+const IniEntry kIniLayout[14] = {
+    {"map pixels", Conv::Int, [](InputParams &q, const std::string &, long i, float) { q.npix = (int)i; }},
+    {"source redshift", Conv::Float, [](InputParams &q, const std::string &, long, float f) { q.zs = f; }},
+    {"field of view", Conv::Float, [](InputParams &q, const std::string &, long, float f) { q.fov = f; }},
+    {"snapshot list", Conv::Text, [](InputParams &q, const std::string &t, long, float) { q.filredshiftlist = t; }},
+    {"snapshot path", Conv::Text, [](InputParams &q, const std::string &t, long, float) { q.pathsnap = t; }},
+    {"simulation name", Conv::Text, [](InputParams &q, const std::string &t, long, float) { q.simulation = t; }},
+    {"seed of the box centres", Conv::Int, [](InputParams &q, const std::string &, long i, float) { q.seedcenter = (int)i; }},
+    // the next two labels are crossed in the reference's example file: entry 8 drives the axis permutation, entry 9 the mirrors
+    {"seed of the axis permutation", Conv::Int, [](InputParams &q, const std::string &, long i, float) { q.seedface = (int)i; }},
+    {"seed of the reflections", Conv::Int, [](InputParams &q, const std::string &, long i, float) { q.seedsign = (int)i; }},
+    {"one map per particle type", Conv::Flag, [](InputParams &q, const std::string &, long i, float) { q.partinplanes = i != 0; }},
+    {"output directory", Conv::Text, [](InputParams &q, const std::string &t, long, float) { q.directory = t; }},
+    {"output suffix", Conv::Text, [](InputParams &q, const std::string &t, long, float) { q.suffix = t; }},
+    {"particle degradation", Conv::Int, [](InputParams &q, const std::string &, long i, float) { q.snopt = (int)i; }},
+    {"dark-energy w", Conv::Float, [](InputParams &q, const std::string &, long, float f) { q.w = f; }},
+};
+} // namespace
+
 int readInput(InputParams &p, const std::string &name)
 {
-  std::ifstream fin(name.c_str());
-  if (!fin.is_open())
-  {
-    std::cerr << " Params file " << name << " does not exist where you are running the code " << std::endl;
-    std::cerr << " I will STOP here!!! " << std::endl;
+  std::ifstream ini(name.c_str());
+  if (!ini)
+  { // the reference leaves the process here as well (data.cpp:13-19)
+    std::cerr << "slicer-b200: cannot open the parameter file '" << name << "'" << std::endl;
     exit(1);
   }
-  std::string str;
-  auto value = [&](std::string &dst) {
-    std::getline(fin, str);
-    std::getline(fin, dst);
-  };
-  std::string v;
-  value(v);
-  p.npix = std::stoi(v); //  1. Number of Pixels
-  value(v);
-  p.zs = std::stof(v); //    2. Redshift Source   (float precision, data.cpp:26)
-  value(v);
-  p.fov = std::stof(v); //   3. Field of View     (float precision, data.cpp:29)
-  value(p.filredshiftlist); // 4.
-  value(p.pathsnap);        // 5.
-  value(p.simulation);      // 6.
-  value(v);
-  p.seedcenter = std::stoi(v); // 7.
-  value(v);
-  p.seedface = std::stoi(v); //   8. (labelled "Pos. Reflec." but drives the axis permutation)
-  value(v);
-  p.seedsign = std::stoi(v); //   9. (labelled "Axis Sel." but drives the reflections)
-  value(v);
-  p.partinplanes = std::stoi(v) != 0; // 10.
-  value(p.directory);                 // 11.
-  value(p.suffix);                    // 12.
-  value(v);
-  p.snopt = std::stoi(v); // 13.
-  value(v);
-  p.w = std::stof(v); //     14.
+  std::vector<std::string> lines;
+  for (std::string l; std::getline(ini, l);)
+    lines.push_back(l);
+  for (int k = 0; k < 14; k++)
+  {
+    // value k sits on line 2k+1 (0-based); a file that ends early yields empty values, which the numeric conversions reject
+    const std::string text = (size_t)(2 * k + 1) < lines.size() ? lines[2 * k + 1] : std::string();
+    const IniEntry &e = kIniLayout[k];
+    long iv = 0;
+    float fv = 0.f;
+    try
+    {
+      if (e.conv == Conv::Int || e.conv == Conv::Flag)
+        iv = std::stoi(text);
+      else if (e.conv == Conv::Float)
+        fv = std::stof(text);
+    }
+    catch (const std::exception &)
+    {
+      std::cerr << "slicer-b200: '" << name << "': entry " << k + 1 << " (" << e.what << ") is not a number: '" << text << "'" << std::endl;
+      throw; // std::stoi / std::stof throw out of the reference's readInput too
+    }
+    e.store(p, text, iv, fv);
+  }
+  // derived fields (data.cpp:60-81): npix == 0 selects the halo branch, npix < 0 asks for a physical pixel size in kpc/h
   p.simType = p.npix == 0 ? "SubFind" : "Gadget";
   p.physical = p.npix < 0;
-  if (!p.physical)
-    p.snpix = sconv_int(p.npix);
-  else
+  p.snpix = sconv_int(p.physical ? -p.npix : p.npix);
+  if (p.physical)
   {
-    const int n = -p.npix;
-    p.snpix = sconv_int(n) + "_kpc";
-    p.rgrid = n;
+    p.snpix += "_kpc";
+    p.rgrid = -p.npix;
   }
   if (p.snopt < 0)
   {
-    std::cerr << "Impossible value for Shot-Noise option!" << std::endl;
+    std::cerr << "slicer-b200: the particle degradation exponent must not be negative (got " << p.snopt << ")" << std::endl;
     return 1;
   }
   return 0;
 }
 
-// gadget2io.cpp:613-661 — including its behaviour at the end of the list (the last name is re-used when the list
-// runs out before a snapshot deeper than the source, App. C)
+// ---------------------------------------------------------------------------------------------------------------
+// The snapshot list (gadget2io.cpp:613-661): whitespace-separated snapshot names in order of increasing redshift; snapshots are
+// taken up to and including the first one at or beyond the source.  One behaviour of the reference's extraction loop is part
+// of the contract: when the list is exhausted before such a snapshot and the file does not end right
+// after the last name, the last snapshot is entered a second time.
+// ---------------------------------------------------------------------------------------------------------------
 int readRedList(const std::string &filredshiftlist, std::vector<double> &snapred, std::vector<std::string> &snappath,
                 std::vector<double> &snapbox, InputParams &p)
 {
-  std::ifstream redlist(filredshiftlist.c_str());
-  double zlast = -999.9;
-  if (!redlist.is_open())
+  std::ifstream in(filredshiftlist.c_str(), std::ios::binary);
+  if (!in)
   {
-    std::cerr << " redshift list file redshift_list.txt does not " << std::endl;
-    std::cerr << " exist in the Code dir ... check this out      " << std::endl;
-    std::cerr << "    I will STOP here !!! " << std::endl;
+    std::cerr << "slicer-b200: cannot open the snapshot list '" << filredshiftlist << "'" << std::endl;
     return 1;
   }
-  std::string name;
-  Header header;
-  do
+  const std::string text((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  std::vector<std::string> names;
+  size_t at = 0, last_end = 0;
+  while (true)
   {
-    redlist >> name;
+    while (at < text.size() && isspace((unsigned char)text[at]))
+      at++;
+    if (at >= text.size())
+      break;
+    size_t e = at;
+    while (e < text.size() && !isspace((unsigned char)text[e]))
+      e++;
+    names.push_back(text.substr(at, e - at));
+    at = last_end = e;
+  }
+  const bool ends_after_last_name = last_end == text.size();
+  if (names.empty())
+    names.push_back(std::string()); // the reference then looks for "<path>.0" and reports it missing
+  // the sequence of names the reference's loop visits
+  std::vector<std::string> visit = names;
+  if (!ends_after_last_name)
+    visit.push_back(names.back());
+  double z_prev = -999.9;
+  for (const std::string &name : visit)
+  {
+    Header hd;
     snappath.push_back(name);
-    if (readHeader(p.pathsnap + name + ".0", header))
+    if (readHeader(p.pathsnap + name + ".0", hd))
     {
-      std::cerr << name << " not found!" << std::endl;
+      std::cerr << "slicer-b200: snapshot '" << name << "' of the list has no readable sub-file 0 under '" << p.pathsnap << "'" << std::endl;
       return 1;
     }
-    if (header.redshift < zlast)
+    if (hd.redshift < z_prev)
     {
-      std::cerr << " Snapshots on " << filredshiftlist << " are not sorted!" << std::endl;
+      std::cerr << "slicer-b200: the snapshots in '" << filredshiftlist << "' must be in order of increasing redshift" << std::endl;
       return 1;
     }
-    zlast = header.redshift;
-    if (std::abs(zlast) < 1e-5)
-      zlast = 0.0;
-    snapred.push_back(zlast);
-    snapbox.push_back(header.boxsize);
-  } while ((header.redshift < p.zs) & (!redlist.eof()));
+    z_prev = std::abs(hd.redshift) < 1e-5 ? 0.0 : hd.redshift;
+    snapred.push_back(z_prev);
+    snapbox.push_back(hd.boxsize);
+    if (!(hd.redshift < p.zs))
+      break; // the first snapshot at or beyond the source closes the list
+  }
   return 0;
 }
 
-// gadget2io.cpp:34-48
+// A Gadget snapshot is "hydro" when some particle type present in sub-file 0 has no entry in the mass table, i.e. carries
+// per-particle masses in a MASS block (gadget2io.cpp:34-48)
 void testHydro(InputParams &p, const Header &data)
 {
-  if (p.simType == "Gadget")
-  {
-    int dimmass0 = 0;
-    for (int i = 0; i <= 5; i++)
-      if (data.massarr[i] == 0)
-        dimmass0 += data.npart[i];
-    p.hydro = dimmass0 != 0;
-  }
+  if (p.simType != "Gadget")
+    return;
+  long with_own_mass = 0;
+  for (int t = 0; t < 6; t++)
+    with_own_mass += data.massarr[t] == 0 ? data.npart[t] : 0;
+  p.hydro = with_own_mass != 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -251,103 +299,128 @@ void CosmoTable::build(double om0, double oml, double w, double zs)
   getZl.init(dl, zl);
 }
 
-// densitymaps.cpp:9-32 — note the float `test` (the comparison is made on a float-rounded distance)
+// The snapshot whose comoving distance is nearest to dlens (densitymaps.cpp:9-32); the first one wins ties.  The reference
+// narrows the separation to FLOAT before comparing, which decides near-ties: kept.
 int getSnap(const std::vector<double> &zsnap, const CubicSpline &getDl, double dlens)
 {
-  if (zsnap.empty())
-    return -1;
-  unsigned pos = 0;
-  double aux = 99999;
-  for (size_t i = 0; i < zsnap.size(); i++)
+  int nearest = -1;
+  double smallest = 99999;
+  for (int i = 0; i < (int)zsnap.size(); i++)
   {
-    const float test = std::abs(getDl.eval(zsnap[i]) - dlens);
-    if (test < aux)
+    const float separation = (float)std::abs(getDl.eval(zsnap[i]) - dlens);
+    if (separation < smallest)
     {
-      aux = test;
-      pos = i;
+      smallest = separation;
+      nearest = i;
     }
   }
-  return pos;
+  return zsnap.empty() ? -1 : (nearest < 0 ? 0 : nearest);
 }
 
-// densitymaps.cpp:46-156
+// ---------------------------------------------------------------------------------------------------------------
+// The light-cone plan (what densitymaps.cpp:46-156 computes).  Planes are stacked outwards from the observer; a plane is
+// 1/numOfLensPerSnap of the box of the snapshot it is cut from.  For every new plane:
+//   1. each snapshot from the current one on is tried as the source of the NEXT plane: the plane would end at
+//      far_i = edge + box_i / L; the snapshot nearest to far_i in comoving distance is a candidate, scored by how far its
+//      redshift is from z(far_i); inside a group of L planes only candidates with the current box size are allowed;
+//   2. the winner fixes the plane's thickness; the plane is finally assigned to the snapshot nearest to its MIDDLE.
+// `edge` is a running sum and every quotient is formed as box / (1e3 / POS_U) / L, as in the reference: the plane edges are
+// part of the output contract (FITS keys DlLOW / DlUP, planes_list) and have to agree to the last bit.
+// ---------------------------------------------------------------------------------------------------------------
+namespace
+{
+struct PlanePlan
+{
+  double near_edge, far_edge; // comoving Mpc/h
+  double z_mid;               // redshift of the plane's middle
+  int snap;                   // index in the snapshot list
+  bool new_group;             // first plane of a randomisation group
+  int run_end;                // 1-based index of the last plane of this plane's run of equal snapshots
+};
+
+inline double slabThickness(double box, int lensPerSnap) { return box / (1e3 / POS_U) / lensPerSnap; }
+
+std::vector<PlanePlan> planLightCone(const std::vector<double> &zsnap, const std::vector<double> &box, const CubicSpline &distOfZ,
+                                     const CubicSpline &zOfDist, int lensPerSnap, double sourceDistance)
+{
+  std::vector<PlanePlan> plan;
+  int current = 0; // snapshot of the previous plane
+  double edge = 0.0;
+  do
+  {
+    const int k = (int)plan.size(); // 0-based index of the plane being planned
+    const bool opens_group = k % lensPerSnap == 0;
+    int winner = current;
+    double best = 9999;
+    for (size_t i = (size_t)current; i < zsnap.size(); i++)
+    {
+      const double far_i = edge + slabThickness(box[i], lensPerSnap);
+      const int cand = getSnap(zsnap, distOfZ, far_i);
+      const double score = fabs(zsnap[cand] - zOfDist.eval(far_i));
+      if (score < best && (opens_group || box[cand] == box[current]))
+      {
+        winner = cand;
+        best = score;
+      }
+    }
+    const double thick = slabThickness(box[winner], lensPerSnap);
+    edge += thick;
+    const double middle = edge - 0.5 * thick;
+    PlanePlan pl;
+    pl.snap = getSnap(zsnap, distOfZ, middle);
+    pl.far_edge = edge;
+    pl.near_edge = edge - slabThickness(box[pl.snap], lensPerSnap);
+    pl.z_mid = zOfDist.eval(middle);
+    pl.new_group = opens_group;
+    pl.run_end = 0;
+    plan.push_back(pl);
+    current = pl.snap;
+  } while (edge < sourceDistance);
+  // runs of consecutive planes cut from the same snapshot: every plane remembers where its run ends
+  for (size_t i = plan.size(); i-- > 0;)
+    plan[i].run_end = (i + 1 < plan.size() && plan[i + 1].snap == plan[i].snap) ? plan[i + 1].run_end : (int)i + 1;
+  return plan;
+}
+} // namespace
+
 int buildPlanes(InputParams &p, Lens &lens, std::vector<double> &snapred, std::vector<std::string> &snappath,
                 std::vector<double> &snapbox, const CubicSpline &getDl, const CubicSpline &getZl, int numOfLensPerSnap, int myid)
 {
-  const size_t nsnaps = snapred.size();
-  int pos = 0, nrepi = 0, nrep = 0;
-  double ldbut = 0.0;
-  do
+  if (snapred.empty())
   {
-    nrep++;
-    nrepi++;
-    double ztest = 9999;
-    int pos_temp = pos;
-    for (size_t i = pos_temp; i < nsnaps; i++)
-    {
-      const double dtest = ldbut + snapbox[i] / (1e3 / POS_U) / numOfLensPerSnap;
-      const int itest = getSnap(snapred, getDl, dtest);
-      if (itest == -1)
-      {
-        std::cerr << "snapred is an empty array!" << std::endl;
-        std::cerr << "Check your snapshot list file." << std::endl;
-        return 1;
-      }
-      const double dz = fabs(snapred[itest] - getZl.eval(dtest));
-      if (dz < ztest)
-        if (nrep == 1 || (!bool((nrep - 1) % numOfLensPerSnap) || snapbox[itest] == snapbox[pos]))
-        {
-          pos_temp = itest;
-          ztest = dz;
-        }
-    }
-    ldbut += snapbox[pos_temp] / (1e3 / POS_U) / numOfLensPerSnap;
-    const double dlens = ldbut - 0.5 * snapbox[pos_temp] / (1e3 / POS_U) / numOfLensPerSnap;
-    const double zlens = getZl.eval(dlens);
-    pos_temp = getSnap(snapred, getDl, dlens);
-    if (myid == 0)
-      std::cout << " simulation snapshots = " << ldbut << "  " << getZl.eval(ldbut) << "  " << nrep << " from snap " << snappath[pos_temp]
-                << "  " << zlens << std::endl;
-    lens.ld.push_back(ldbut - snapbox[pos_temp] / (1e3 / POS_U) / numOfLensPerSnap);
-    lens.ld2.push_back(ldbut);
-    lens.zfromsnap.push_back(snapred[pos_temp]);
-    if (nrep != 1 && pos_temp != pos)
-    {
-      for (int i = 0; i < nrepi - 1; i++)
-        lens.replication.push_back(nrep - 1);
-      nrepi = 1;
-    }
-    pos = pos_temp;
-    lens.zsimlens.push_back(zlens);
-    lens.fromsnap.push_back(snappath[pos]);
-    lens.fromsnapi.push_back(pos);
-    lens.randomize.push_back(nrep == 1 ? true : !((nrep - 1) % numOfLensPerSnap));
-  } while (ldbut < p.Ds);
-  for (int i = 0; i < nrepi + 1; i++)
-    lens.replication.push_back(nrep);
-  if (myid == 0)
-  {
-    std::cout << " Comoving Distance of the last plane " << p.Ds << std::endl;
-    std::cout << " nsnaps = " << nsnaps << "\n" << std::endl;
+    std::cerr << "slicer-b200: the snapshot list is empty, there is nothing to plan" << std::endl;
+    return 1;
   }
-  std::ofstream planelist;
-  const std::string planes_list = p.directory + "planes_list_" + p.suffix + ".txt";
-  if (myid == 0)
-    planelist.open(planes_list.c_str());
-  for (size_t i = 0; i < lens.fromsnap.size(); i++)
+  const std::vector<PlanePlan> plan = planLightCone(snapred, snapbox, getDl, getZl, numOfLensPerSnap, p.Ds);
+  const int total = (int)plan.size();
+  for (const PlanePlan &pl : plan)
   {
-    if (myid == 0)
-    {
-      std::cout << lens.zsimlens[i] << " planes = " << lens.ld[i] << "  " << lens.ld2[i] << "  " << lens.replication[i] << " from snap "
-                << lens.fromsnap[i] << std::endl;
-      planelist << i << "   " << lens.zsimlens[i] << "   " << lens.ld[i] << "   " << lens.ld2[i] << "   " << lens.replication[i] << "   "
-                << lens.fromsnap[i] << "   " << lens.zfromsnap[i] << "  " << lens.randomize[i] << std::endl;
-    }
-    lens.pll.push_back(i);
+    lens.ld.push_back(pl.near_edge);
+    lens.ld2.push_back(pl.far_edge);
+    lens.zsimlens.push_back(pl.z_mid);
+    lens.zfromsnap.push_back(snapred[pl.snap]);
+    lens.fromsnap.push_back(snappath[pl.snap]);
+    lens.fromsnapi.push_back(pl.snap);
+    lens.randomize.push_back(pl.new_group);
+    lens.replication.push_back(pl.run_end);
+    lens.pll.push_back((int)lens.pll.size());
   }
-  if (myid == 0)
-    planelist.close();
-  lens.nplanes = lens.replication.back();
+  lens.replication.push_back(total); // Lens.replication carries one entry more than there are planes (data.h:108); its last is nplanes
+  lens.nplanes = total;
+  if (myid != 0)
+    return 0;
+  // report + planes_list_<suffix>.txt: one row per plane, columns as Lens/kslicer.py:29 reads them
+  //   index   z(middle)   near edge   far edge   last plane of the snapshot run   snapshot   z(snapshot)  first of a group
+  std::cout << " light cone to " << p.Ds << " Mpc/h comoving: " << total << " planes from " << snapred.size() << " snapshots" << std::endl;
+  std::ofstream list((p.directory + "planes_list_" + p.suffix + ".txt").c_str());
+  for (int i = 0; i < total; i++)
+  {
+    const PlanePlan &pl = plan[i];
+    std::cout << "   plane " << i << ": " << pl.near_edge << " - " << pl.far_edge << " Mpc/h, z = " << pl.z_mid << ", cut from " << snappath[pl.snap]
+              << (pl.new_group ? "  [new randomisation]" : "") << std::endl;
+    list << i << "   " << pl.z_mid << "   " << pl.near_edge << "   " << pl.far_edge << "   " << pl.run_end << "   " << snappath[pl.snap] << "   "
+         << snapred[pl.snap] << "  " << pl.new_group << std::endl;
+  }
   return 0;
 }
 
@@ -385,89 +458,86 @@ GlibcRand &sharedRand()
   return g;
 }
 
-// densitymaps.cpp:166-248 — the reference uses libc srand/rand; GlibcRand is the same generator with private state
+// The randomisation of every group of planes (what densitymaps.cpp:166-248 draws with libc srand/rand; GlibcRand is the same
+// generator with private state): three streams, re-seeded per group with seed + group * {13, 5, 8}: the box centre (three
+// uniform draws), the axis permutation `face` in 1..6 (redrawn until in range) and the three mirror signs.  A uniform draw is
+// rand() / float(RAND_MAX), a FLOAT division by 2147483648.f.  Planes inside a group inherit the group's values.
 void randomizeBox(Random &random, const Lens &lens, const InputParams &p, int numOfLensPerSnap, int myid, bool fixedVertex)
 {
-  const size_t nrandom = lens.replication.back();
-  random.x0.resize(nrandom);
-  random.y0.resize(nrandom);
-  random.z0.resize(nrandom);
-  random.sgnX.resize(nrandom);
-  random.sgnY.resize(nrandom);
-  random.sgnZ.resize(nrandom);
-  random.face.resize(nrandom);
-  for (size_t i = 0; i < nrandom; i++)
+  struct Draw
+  {
+    double centre[3];
+    int face;
+    int sign[3];
+  };
+  auto uniform = [](GlibcRand &g) { return g.next() / float(RAND_MAX); };
+  const size_t count = lens.replication.back();
+  std::vector<int> *const signs[3] = {&random.sgnX, &random.sgnY, &random.sgnZ};
+  std::vector<double> *const centres[3] = {&random.x0, &random.y0, &random.z0};
+  for (int k = 0; k < 3; k++)
+  {
+    signs[k]->assign(count, 0);
+    centres[k]->assign(count, 0.0);
+  }
+  random.face.assign(count, 0);
+  Draw d = {};
+  for (size_t i = 0; i < count; i++)
   {
     if (lens.randomize[i])
     {
-      GlibcRand &R = sharedRand();
-      R.seed(p.seedcenter + i / numOfLensPerSnap * 13);
-      if (!fixedVertex)
-      {
-        random.x0[i] = R.next() / float(RAND_MAX);
-        random.y0[i] = R.next() / float(RAND_MAX);
-        random.z0[i] = R.next() / float(RAND_MAX);
-      }
-      else
-      { // -DFixedPLCVertex, densitymaps.cpp:191-195
-        random.x0[i] = 0.0;
-        random.y0[i] = 0.0;
-        random.z0[i] = 0.5;
-      }
-      random.face[i] = 7;
-      R.seed(p.seedface + i / numOfLensPerSnap * 5);
-      while (random.face[i] > 6 || random.face[i] < 1)
-        random.face[i] = int(1 + R.next() / float(RAND_MAX) * 5. + 0.5);
-      R.seed(p.seedsign + i / numOfLensPerSnap * 8);
-      int *sg[3] = {&random.sgnX[i], &random.sgnY[i], &random.sgnZ[i]};
+      GlibcRand &g = sharedRand();
+      const unsigned group = (unsigned)(i / numOfLensPerSnap);
+      g.seed(p.seedcenter + group * 13);
+      for (int k = 0; k < 3; k++)
+        d.centre[k] = fixedVertex ? (k == 2 ? 0.5 : 0.0) : (double)uniform(g); // -DFixedPLCVertex: the vertex sits on a box face
+      g.seed(p.seedface + group * 5);
+      do
+        d.face = int(1 + uniform(g) * 5. + 0.5);
+      while (d.face < 1 || d.face > 6);
+      g.seed(p.seedsign + group * 8);
       for (int k = 0; k < 3; k++)
       {
-        *sg[k] = 2;
-        while (*sg[k] > 1 || *sg[k] < 0)
-          *sg[k] = int(R.next() / float(RAND_MAX) + 0.5);
-        if (*sg[k] == 0)
-          *sg[k] = -1;
+        int bit;
+        do
+          bit = int(uniform(g) + 0.5);
+        while (bit < 0 || bit > 1);
+        d.sign[k] = bit ? 1 : -1;
       }
     }
-    else
+    for (int k = 0; k < 3; k++)
     {
-      random.x0[i] = random.x0[i - 1];
-      random.y0[i] = random.y0[i - 1];
-      random.z0[i] = random.z0[i - 1];
-      random.face[i] = random.face[i - 1];
-      random.sgnX[i] = random.sgnX[i - 1];
-      random.sgnY[i] = random.sgnY[i - 1];
-      random.sgnZ[i] = random.sgnZ[i - 1];
+      (*centres[k])[i] = d.centre[k];
+      (*signs[k])[i] = d.sign[k];
     }
+    random.face[i] = d.face;
     if (myid == 0)
-      std::cout << " plane " << i << " centre " << random.x0[i] << " " << random.y0[i] << " " << random.z0[i] << " face " << random.face[i]
-                << " signs " << random.sgnX[i] << " " << random.sgnY[i] << " " << random.sgnZ[i] << std::endl;
+      std::cout << "   plane " << i << ": centre (" << d.centre[0] << ", " << d.centre[1] << ", " << d.centre[2] << "), axis permutation " << d.face
+                << ", mirrors (" << d.sign[0] << ", " << d.sign[1] << ", " << d.sign[2] << ")" << std::endl;
   }
 }
 
-// densitymaps.cpp:255-269 — only rank 0 reports the failure (quirk iii of App. D.7 kept)
+// The field must fit into one box at the far edge of the plane (densitymaps.cpp:255-269): fov [rad] * distance <= box.  As in the
+// reference only rank 0 reports (and returns) the failure.
 int testFov(double fov, double boxl, double Ds, int myid, double &fovradiants)
 {
   fovradiants = fov / 180. * M_PI;
-  if ((fovradiants)*Ds > boxl && myid == 0)
+  const bool too_wide = fovradiants * Ds > boxl;
+  if (too_wide && myid == 0)
   {
-    std::cerr << " !!Field view too large!!\n !!!I will STOP here!!! " << std::endl;
-    std::cerr << " Value set is = " << fov << std::endl;
-    std::cerr << " Maximum value allowed " << boxl / Ds * 180. / M_PI << " in degrees " << std::endl;
-    std::cerr << " For the lens at " << Ds << std::endl;
+    std::cerr << "slicer-b200: a field of " << fov << " deg does not fit into the " << boxl << " Mpc/h box at " << Ds
+              << " Mpc/h (at most " << boxl / Ds * 180. / M_PI << " deg); build with replication on the perpendicular plane for wider fields"
+              << std::endl;
     return 1;
   }
   return 0;
 }
 
-// densitymaps.cpp:275-283
+// Box copies needed on either side, perpendicular to the line of sight, for the field at distance Ds (densitymaps.cpp:275-283)
 void computeReplications(double fov, double boxl, double Ds, int, double &fovradiants, int &nrepperp)
 {
   fovradiants = fov / 180. * M_PI;
-  if (Ds * tan(fovradiants / 2.0) <= boxl / 2.0)
-    nrepperp = 0;
-  else
-    nrepperp = ceil((Ds * tan(fovradiants / 2) - boxl / 2.0) / boxl);
+  const double half_width = Ds * tan(fovradiants / 2.0);
+  nrepperp = half_width <= boxl / 2.0 ? 0 : (int)ceil((Ds * tan(fovradiants / 2) - boxl / 2.0) / boxl);
 }
 
 } // namespace slicer

@@ -1,5 +1,5 @@
-"""Multi-rank plumbing around the C ABI (one process per GPU): everything here is host logic and runs on any
-torch.distributed backend (NCCL on the GPU box, gloo in the CPU tests)."""
+"""Test-side helpers for the multi-rank host logic (one process per GPU): everything here runs on any torch.distributed
+backend (gloo in the CPU tests).  Not part of the product package."""
 from __future__ import annotations
 
 from typing import List, Tuple

@@ -8,7 +8,14 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from slicer_b200 import dist as sdist
+sys_path_root = os.path.dirname(os.path.abspath(__file__))
+import sys
+
+if sys_path_root not in sys.path:
+    sys.path.insert(0, sys_path_root)
+if os.path.dirname(sys_path_root) not in sys.path:
+    sys.path.insert(0, os.path.dirname(sys_path_root))
+import dist_helpers as sdist  # noqa: E402  (test-side helpers: rank plumbing on any torch.distributed backend)
 
 
 def _worker(rank, world, port, q):
@@ -32,11 +39,21 @@ def _worker(rank, world, port, q):
         mine = sdist.balanced_subfiles(n, world, rank)
         part = orc.gridist_w_fixed(xs[mine], ys[mine], ms[mine], nn, 40)
         total = sdist.sum_int64_planes(part)
+        # the bench's hardware check of ncclReduce(int64): linear checksums of the per-rank planes add up to the reduced plane's
+        import bench
+
+        mine_cs = torch.tensor([v - (1 << 64) if v >= (1 << 63) else v for v in bench.linear_checksums(part)], dtype=torch.int64)
+        allcs = [torch.zeros_like(mine_cs) for _ in range(world)]
+        dist.all_gather(allcs, mine_cs)
+        lo, hi = bench.shard_range(1000003, world, rank)
         if rank == 0:
             full = orc.gridist_w_fixed(xs, ys, ms, nn, 40)
-            q.put(dict(uid_ok=uid == bytes(range(128)), tmax=t, exact=bool(np.array_equal(total.numpy(), full))))
+            got = bench.linear_checksums(total.numpy())
+            want = tuple(sum(int(c[k]) for c in allcs) & ((1 << 64) - 1) for k in range(2))
+            q.put(dict(uid_ok=uid == bytes(range(128)), tmax=t, exact=bool(np.array_equal(total.numpy(), full)), checks=got == want,
+                       shard=(lo, hi)))
         else:
-            q.put(dict(uid_ok=uid == bytes(range(128)), tmax=t))
+            q.put(dict(uid_ok=uid == bytes(range(128)), tmax=t, shard=(lo, hi)))
     finally:
         dist.destroy_process_group()
 
@@ -54,6 +71,9 @@ def test_two_rank_plumbing():
         assert p.exitcode == 0
     assert all(r["uid_ok"] for r in res) and all(r["tmax"] == 2.0 for r in res)
     assert any(r.get("exact") for r in res)
+    assert any(r.get("checks") for r in res)
+    shards = sorted(r["shard"] for r in res)
+    assert shards[0][0] == 0 and shards[0][1] == shards[1][0] and shards[1][1] == 1000003 and shards[0][1] % 4 == 0
 
 
 def test_subfile_split_matches_reference():
