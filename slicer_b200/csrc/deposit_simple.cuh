@@ -11,7 +11,7 @@
 
 template <int MAS>
 __global__ void __launch_bounds__(256) deposit_simple_kernel(const __grid_constant__ PassParams P,
-                                                             const __grid_constant__ SegmentDev S)
+                                                             const __grid_constant__ SegmentDev S, const __grid_constant__ DeferDev F)
 {
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < S.n; i += stride)
@@ -58,12 +58,15 @@ __global__ void __launch_bounds__(256) deposit_simple_kernel(const __grid_consta
             if (!chain::prefilter(x, y, z, ni, nj, L))
               continue;
             float xs, ys;
-            if (chain::project_accept(x, y, z, ni, nj, L, xs, ys))
+            bool amb = false;
+            if (chain::project_accept(x, y, z, ni, nj, L, xs, ys, &amb))
             {
               atomicAdd(&cnt[0], 1ull); // mapParticles' totPartxyi (densitymaps.cpp:402)
               if (chain::deposit<MAS>(xs, ys, m, L, map))
                 atomicAdd(&cnt[1], 1ull);
             }
+            else if (amb) // within the rounding guard of a decision: the host's libm settles it
+              chain::defer_push(F, __fadd_rn(x, (float)ni), __fadd_rn(y, (float)nj), z, m, q, S.type);
           }
       }
     }

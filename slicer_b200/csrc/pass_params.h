@@ -70,6 +70,8 @@ struct PlaneDev
   double scale;      // 2^frac_bits
   float scalef;      // the same as a float (exact)
   float dlf, half_dlf, onehalf_dlf; // float copies of dl, 0.5*dl, 1.5*dl: exact when npix is a power of two
+  double guard_eta;  // rounding guard on dec/fov + 0.5 (slicer_config::guard_eta, default 2^-47) ...
+  double guard_T;    // ... and on |ra|, |dec| against T: decisions inside the guard are settled with the host's libm
   double arg_lim;    // small-angle series: valid (and sufficient) for |X/d|, |Y/Z| <= arg_lim
   int nt;            // terms of the small-angle series, 0 => use libdevice asin/atan2 (wide fields)
   unsigned long long *acc;    // this plane's accumulators: [ntypes_alloc][npix*npix] int64 fixed point

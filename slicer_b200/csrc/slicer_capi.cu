@@ -771,6 +771,8 @@ static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int npl
       // small-angle series for asin/atan (device_chain.cuh): enough terms that arg_lim^(2 nt) < 2^-55
       L.nt = 0;
       L.arg_lim = 0;
+      L.guard_eta = h->cfg.guard_eta >= LEAN_ETA ? h->cfg.guard_eta : LEAN_ETA;
+      L.guard_T = 2.0 * L.guard_eta * L.T; // an angle is (map coordinate - 0.5) * fov: the same guard, in radians
       if (!h->no_series && isfinite(L.pre_tx) && (double)L.pre_tx * 1.01 <= 0.385)
       {
         L.arg_lim = (double)L.pre_tx * 1.01;
@@ -1184,8 +1186,7 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
   F.count = h->defer.count;
   F.cap = h->defer.cap;
   F.pass = (unsigned)h->defer.passes.size();
-  if (P.lean.enabled)
-  {
+  { // (any path can defer pairs: the lean projection and the general chain's guard)
     slicer_handle::SavedPass sp;
     sp.P = P;
     for (int k = 0; k < P.nplanes; k++)
@@ -1222,9 +1223,9 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
       size_t cap = (size_t)h->sm_count * 8;
       int blocks = (int)(want < cap ? want : cap);
       if (h->cfg.mas == SLICER_MAS_NGP)
-        deposit_simple_kernel<SLICER_MAS_NGP><<<blocks, 256, 0, h->compute>>>(P, D);
+        deposit_simple_kernel<SLICER_MAS_NGP><<<blocks, 256, 0, h->compute>>>(P, D, F);
       else
-        deposit_simple_kernel<SLICER_MAS_TSC><<<blocks, 256, 0, h->compute>>>(P, D);
+        deposit_simple_kernel<SLICER_MAS_TSC><<<blocks, 256, 0, h->compute>>>(P, D, F);
       CU(cudaGetLastError());
     }
     h->stats.launches++;

@@ -11,6 +11,7 @@
 #include <fstream>
 #include <iostream>
 #include <memory>
+#include <sstream>
 #include <thread>
 
 namespace slicer
@@ -29,6 +30,7 @@ struct Engine
   int npix_max = 0, mas = SLICER_MAS_TSC, deposit_mode = SLICER_DEPOSIT_AUTO;
   bool per_type = false;
   size_t capacity = 0;
+  int max_planes = SLICER_MAX_PLANES; // accumulators per GPU: the most planes one snapshot feeds
   bool comm = false;
 };
 
@@ -45,7 +47,7 @@ static int make_handles(Engine *e)
     cfg.device = e->devices[g];
     cfg.mas = e->mas;
     cfg.max_m = MAX_M;
-    cfg.max_planes = SLICER_MAX_PLANES;
+    cfg.max_planes = e->max_planes;
     cfg.npix_max = e->npix_max;
     cfg.per_type_maps = e->per_type;
     cfg.particle_capacity = e->capacity;
@@ -71,10 +73,12 @@ static int make_handles(Engine *e)
   return 0;
 }
 
-Engine *engineCreate(const std::vector<int> &devices, int npix_max, int mas, bool per_type_maps, size_t particle_capacity, int deposit_mode)
+Engine *engineCreate(const std::vector<int> &devices, int npix_max, int mas, bool per_type_maps, size_t particle_capacity, int deposit_mode,
+                     int max_planes)
 {
   Engine *e = new Engine;
   e->devices = devices;
+  e->max_planes = std::min(std::max(max_planes, 1), (int)SLICER_MAX_PLANES);
   e->npix_max = npix_max;
   e->mas = mas;
   e->per_type = per_type_maps;
@@ -145,6 +149,31 @@ static int stage_subfile(slicer_handle *h, const SubFile &buf, bool hydro)
   return 0;
 }
 
+// The device staging pools must hold the largest sub-file of the snapshot (sub-files of one snapshot differ by tens of per cent
+// with domain decomposition or gas).  The sub-file headers are scanned first (256 bytes each); if one needs more room than the
+// handles have, the handles are rebuilt with that capacity before any work of this snapshot is queued.
+static int ensure_capacity(Engine *e, const std::string &File, unsigned ffmin, unsigned ffmax)
+{
+  size_t largest = 0;
+  for (unsigned ff = ffmin; ff < ffmax; ff++)
+  {
+    Header hd;
+    if (readHeader(File + "." + std::to_string(ff), hd))
+      return 1;
+    size_t n = 0;
+    for (int t = 0; t < 6; t++)
+      n += (size_t)(hd.npart[t] > 0 ? hd.npart[t] : 0);
+    largest = std::max(largest, n);
+  }
+  if (largest <= e->capacity)
+    return 0;
+  for (auto *hh : e->h)
+    if (hh && slicer_synchronize(hh))
+      return fail_capi("slicer_synchronize");
+  e->capacity = largest + largest / 8 + 4096;
+  return make_handles(e);
+}
+
 // `Part. Degradation` (snopt > 0, densitymaps.cpp:387-397).  The reference consumes one libc rand() per accepted
 // (particle, replica) pair, plane after plane, sub-file after sub-file, type after type, particle after particle —
 // one serial stream that continues from randomizeBox's last srand().  Sweep 1 counts the accepted pairs of every
@@ -155,9 +184,9 @@ static int createDensityMapsDegraded(Engine *e, InputParams &p, Lens &lens, Rand
                                      std::vector<std::valarray<float>> &mapxytoti, std::vector<long long> &ntotxyi, int myid)
 {
   const int nj = (int)jobs.size();
-  if (nj > SLICER_MAX_PLANES)
+  if (nj > e->max_planes)
   {
-    std::cerr << "Part. Degradation: more than " << SLICER_MAX_PLANES << " planes share one snapshot; not supported" << std::endl;
+    std::cerr << "Part. Degradation: more than " << e->max_planes << " planes share one snapshot; not supported" << std::endl;
     return 1;
   }
   mapxytot.assign(nj, std::valarray<float>());
@@ -168,6 +197,8 @@ static int createDensityMapsDegraded(Engine *e, InputParams &p, Lens &lens, Rand
   std::vector<slicer_plane_desc> descs;
   for (int j = 0; j < nj; j++)
     descs.push_back(make_desc(lens, random, jobs[j].isnap, jobs[j].rcase, fovradiants, jobs[j].npix));
+  if (ensure_capacity(e, File, ffmin, ffmax))
+    return 1;
   // ---- sweep 1: accepted pairs per (plane, sub-file, type)
   std::vector<long long> cnt((size_t)nff * nj * 6, 0);
   for (unsigned ff = ffmin; ff < ffmax; ff++)
@@ -271,63 +302,85 @@ int createDensityMapsMulti(Engine *e, InputParams &p, Lens &lens, Random &random
   mapxytoti.assign((size_t)njobs * 6, std::valarray<float>());
   ntotxyi.assign((size_t)njobs * 6, 0);
   const int ngpu = (int)e->h.size();
-  for (int j0 = 0; j0 < njobs; j0 += SLICER_MAX_PLANES)
+  for (int j0 = 0; j0 < njobs; j0 += e->max_planes)
   {
-    const int nj = std::min(njobs - j0, (int)SLICER_MAX_PLANES);
+    const int nj = std::min(njobs - j0, e->max_planes);
     std::vector<slicer_plane_desc> descs;
     for (int j = 0; j < nj; j++)
       descs.push_back(make_desc(lens, random, jobs[j0 + j].isnap, jobs[j0 + j].rcase, fovradiants, jobs[j0 + j].npix));
     std::fill(e->used.begin(), e->used.end(), 0);
     Header first_header;
     bool have_header = false;
-    for (unsigned ff = ffmin; ff < ffmax; ff++)
+    if (ffmax > ffmin && readHeader(File + "." + std::to_string(ffmin), first_header) == 0)
+      have_header = true;
+    // One host thread per GPU (the reference: one MPI rank per group of sub-files, slicer-v2.cpp:162-175, densitymaps.cpp:432-484):
+    // GPU g takes sub-files ffmin + g, ffmin + g + ngpu, ...; it reads sub-file k+1 into its second page-locked buffer while the
+    // copy and the pass of sub-file k run.  Messages are collected per thread and printed in sub-file order afterwards.
+    std::vector<int> rcs(ngpu, 0);
+    std::vector<std::string> logs(ngpu), errs(ngpu);
+    std::vector<double> read_s(ngpu, 0.0);
+    auto work = [&](int g) {
+      std::ostringstream log, err;
+      for (unsigned ff = ffmin + (unsigned)g; ff < ffmax && !rcs[g]; ff += (unsigned)ngpu)
+      {
+        SubFile &buf = e->bufs[2 * g + (e->used[g] & 1)];
+        if (e->used[g] >= 2 && slicer_wait_staging(e->h[g])) // the copy that last read this host buffer must be done
+        {
+          err << "slicer_wait_staging: " << slicer_last_error() << "\n";
+          rcs[g] = 1;
+          break;
+        }
+        const double tr0 = now_s();
+        if (readSubFile(File + "." + std::to_string(ff), p.hydro, buf, true))
+        {
+          rcs[g] = 1;
+          break;
+        }
+        read_s[g] += now_s() - tr0;
+        const Header &data = buf.header;
+        if (buf.ntotal > e->capacity)
+        { // cannot happen after the header scan of ensure_capacity() unless the file changed in between
+          err << "sub-file " << ff << " holds " << buf.ntotal << " particles, more than the engine's capacity " << e->capacity << "\n";
+          rcs[g] = 1;
+          break;
+        }
+        log << " sub-file " << ff << ": " << buf.ntotal << " particles -> GPU " << e->devices[g] << "\n";
+        int rc = e->used[g] == 0 ? slicer_begin_snapshot(e->h[g], data.boxsize, data.massarr, p.hydro) : slicer_next_batch(e->h[g]);
+        if (!rc)
+          rc = stage_subfile(e->h[g], buf, p.hydro);
+        if (!rc)
+          rc = e->used[g] == 0 ? slicer_deposit(e->h[g], descs.data(), nj) : slicer_deposit_accumulate(e->h[g], descs.data(), nj);
+        if (rc)
+        {
+          err << "GPU " << e->devices[g] << ", sub-file " << ff << ": " << slicer_last_error() << "\n";
+          rcs[g] = 1;
+          break;
+        }
+        e->used[g]++;
+      }
+      logs[g] = log.str();
+      errs[g] = err.str();
+    };
+    if (ensure_capacity(e, File, ffmin, ffmax))
+      return 1;
+    if (ngpu == 1)
+      work(0);
+    else
     {
-      const int g = (int)((ff - ffmin) % ngpu);
-      SubFile &buf = e->bufs[2 * g + (e->used[g] & 1)];
-      if (e->used[g] >= 2 && slicer_wait_staging(e->h[g])) // the copy that last read this host buffer must be done
-        return fail_capi("slicer_wait_staging");
-      const double tr0 = now_s();
-      if (readSubFile(File + "." + std::to_string(ff), p.hydro, buf, true))
-        return 1;
-      t_read += now_s() - tr0;
-      const Header &data = buf.header;
-      if (!have_header)
-      {
-        first_header = data;
-        have_header = true;
-      }
-      if (buf.ntotal > e->capacity)
-      { // a larger sub-file than any seen so far: grow the device pools (rare; finishes pending work first)
-        if (e->used[0] || ff != ffmin)
-        {
-          std::cerr << "sub-file " << ff << " holds " << buf.ntotal << " particles, more than the engine's capacity " << e->capacity << std::endl;
-          return 1;
-        }
-        e->capacity = buf.ntotal + buf.ntotal / 8;
-        if (make_handles(e))
-          return 1;
-      }
+      std::vector<std::thread> th;
+      for (int g = 0; g < ngpu; g++)
+        th.emplace_back(work, g);
+      for (auto &t : th)
+        t.join();
+    }
+    for (int g = 0; g < ngpu; g++)
+    {
+      t_read += read_s[g] / ngpu;
       if (myid == 0)
-        std::cout << " sub-file " << ff << ": " << buf.ntotal << " particles -> GPU " << e->devices[g] << std::endl;
-      int rc = e->used[g] == 0 ? slicer_begin_snapshot(e->h[g], data.boxsize, data.massarr, p.hydro) : slicer_next_batch(e->h[g]);
-      if (rc)
-        return fail_capi("slicer_begin_snapshot");
-      size_t off = 0;
-      for (int t = 0; t < 6; t++)
-      {
-        const size_t nt = (size_t)data.npart[t];
-        if (nt)
-        {
-          const bool pm = p.hydro && data.massarr[t] == 0;
-          if (slicer_stage_particles(e->h[g], t, buf.pos + 3 * off, SLICER_LAYOUT_AOS, pm ? buf.mass + off : nullptr, nt))
-            return fail_capi("slicer_stage_particles");
-        }
-        off += nt;
-      }
-      rc = e->used[g] == 0 ? slicer_deposit(e->h[g], descs.data(), nj) : slicer_deposit_accumulate(e->h[g], descs.data(), nj);
-      if (rc)
-        return fail_capi("slicer_deposit");
-      e->used[g]++;
+        std::cout << logs[g];
+      std::cerr << errs[g];
+      if (rcs[g])
+        return 1;
     }
     for (int g = 0; g < ngpu; g++)
       if (e->used[g] == 0)
@@ -502,7 +555,16 @@ int runLightCone(const std::string &inifile, const RunOptions &opt)
           tot += (size_t)snapdata.npartTotal[i] + ((size_t)(uint32_t)snapdata.nTotalHW[i] << 32);
         const size_t cap = tot / std::max(1, snapdata.numfiles) * 5 / 4 + 65536;
         const double te0 = now_s();
-        e = engineCreate(opt.devices, npix_max, opt.mas, p.partinplanes, cap, opt.deposit_mode);
+        int most = 1; // the most planes one snapshot feeds
+        for (int a = 0; a < lens.nplanes;)
+        {
+          int b = a + 1;
+          while (b < lens.nplanes && lens.fromsnapi[b] == lens.fromsnapi[a])
+            b++;
+          most = std::max(most, b - a);
+          a = b;
+        }
+        e = engineCreate(opt.devices, npix_max, opt.mas, p.partinplanes, cap, opt.deposit_mode, most);
         t_engine += now_s() - te0;
         if (!e)
         {

@@ -155,7 +155,7 @@ int readSubFile(const std::string &file, bool hydro, SubFile &out, bool pinned);
 // ---- the map makers ----------------------------------------------------------------------------------------
 struct Engine; // one handle per GPU + staging buffers
 Engine *engineCreate(const std::vector<int> &devices, int npix_max, int mas, bool per_type_maps, size_t particle_capacity,
-                     int deposit_mode = SLICER_DEPOSIT_AUTO);
+                     int deposit_mode = SLICER_DEPOSIT_AUTO, int max_planes = SLICER_MAX_PLANES);
 void engineDestroy(Engine *e);
 int engineGpuCount(const Engine *e);
 

@@ -709,3 +709,35 @@ def test_binned_per_particle_mass_without_mass_capacity(oracle):
     assert out[capi.DEPOSIT_BINNED].sum() > 0
     assert np.array_equal(out[capi.DEPOSIT_DIRECT], out[capi.DEPOSIT_BINNED])
     assert np.array_equal(out[capi.DEPOSIT_BINNED], res["fixed"][0])
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_rounding_guard_of_the_general_chain(oracle, kernel):
+    """The general chain (one-thread-per-particle baseline kernel; pipelined passes with perpendicular replication or maps that
+    are not a power of two) evaluates asin / atan on the device, within 2 ulp of glibc's.  Pairs for which that could change the
+    field test or the float map coordinate are handed to the host's libm as well (chain::project_accept `amb`).  With the guard
+    widened to 2^-34 thousands of pairs go that way: counts and int64 maps must equal the oracle's, replicas included."""
+    box = 100000.0
+    n = 1 << 20
+    pos = synth.uniform_positions(n, box, 23)
+    types = [dict(type=1, raw=pos, const_mass=0.77)]
+    plane = dict(boxsize=box, sgn=[1, -1, -1], face=6, centre=[0.3, 0.9, 0.1], rcase=1.0, ld=110.0, ld2=190.0, nrepperp=1, fovradiants=0.9)
+    npix = 200
+    res = None
+    for eta in (0.0, 2.0 ** -34):
+        with capi.Slicer(npix_max=npix, max_planes=1, mas=capi.MAS_TSC, particle_capacity=n + 64, kernel=kernel, guard_eta=eta) as s:
+            s.begin_snapshot(box, [0, 0.77, 0, 0, 0, 0], False)
+            s.stage(1, pos)
+            s.deposit([capi.plane_desc(plane["sgn"], plane["face"], plane["centre"], plane["rcase"], plane["ld"], plane["ld2"], plane["fovradiants"],
+                                       npix, nrepperp=1)])
+            fixed = s.fetch_fixed(0, -1, npix).reshape(-1)
+            _, counts, ingrid = s.fetch(0, -1, npix, want_map=False)
+            flagged = int(s.stats().flagged_pairs)
+            fb = s.frac_bits
+        if res is None:
+            res = oracle.plane_from_particles(types, plane, npix, frac_bits=fb)
+            assert res["counts"][1] > 500_000
+        assert counts.tolist() == res["counts"].tolist() and ingrid.tolist() == res["ingrid"].tolist()
+        assert np.array_equal(fixed, res["fixed"][1])
+        if eta:
+            assert flagged > 5_000

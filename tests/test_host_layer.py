@@ -116,6 +116,36 @@ def test_fits_writer_layout(tmp_path):
     assert host.write_fits(f, img, [], []) == 1  # an existing file is not overwritten (FITS::CantCreate)
 
 
+def test_fits_output_conforms_to_the_standard(tmp_path):
+    """The plane files are read by astropy in Lens/kslicer.py:39-40,84-86 (DLLOW, DLUP, PHYSICALSIZE, NAXIS1/2; case-insensitive,
+    HIERARCH-transparent).  astropy / CFITSIO are not on this box, so tests/fits_standard.py restates what a conforming reader
+    checks (FITS 4.0 + the HIERARCH convention) independently of the repo's own reader, and validates a file with the full key
+    set of writeMaps (densitymaps.cpp:563-583), awkward values included."""
+    import fits_standard
+
+    rng = np.random.default_rng(3)
+    img = (rng.random((37, 37)) * 1e3).astype(np.float32)
+    img[0, 0], img[36, 36], img[5, 7] = 0.0, np.float32(3.4e38), np.float32(1e-38)
+    dkeys = [("REDSHIFT", 0.059314673648001914), ("PHYSICALSIZE", 2.0), ("PIXELUNIT", 14285714285.714287), ("DlLOW", 228.57142857142858),
+             ("DlUP", 274.28571428571428), ("HUBBLE", 0.7), ("OMEGAMATTER", 0.3), ("OMEGALAMBDA", 0.7)] + \
+            [(f"m{i}", v) for i, v in enumerate([0.0, 1.0375, 0.0, 0.0, 1e-300, 123456789012.5])]
+    ikeys = [(f"nparttype{i}", v) for i, v in enumerate([0, 1224, 0, 0, 2 ** 40, 7])]
+    f = str(tmp_path / "gadget.041.plane_37_t.fits")
+    assert host.write_fits(f, img, dkeys, ikeys) == 0
+    hdr, rows = fits_standard.read_primary_image(f)
+    assert (hdr["BITPIX"], hdr["NAXIS"], hdr["NAXIS1"], hdr["NAXIS2"]) == (-32, 2, 37, 37)
+    # the keys the consumer reads, the way it spells them
+    assert hdr["DLLOW"] == 228.57142857142858 and hdr["DLUP"] == 274.28571428571428 and hdr["PHYSICALSIZE"] == 2.0
+    for k, v in dkeys:
+        assert hdr[k] == v, k          # %.17G round-trips every double
+    for k, v in ikeys:
+        assert hdr[k] == v and isinstance(hdr[k], int), k
+    assert np.array_equal(np.array(rows, np.float32), img)  # row gy holds map[gx + npix*gy], gx fastest
+    # and the repo's own test reader agrees with the independent one
+    h2, back = host.read_fits(f)
+    assert np.array_equal(back, img) and h2["DlLOW"] == hdr["DLLOW"]
+
+
 def test_glibc_rand_restatement_matches_libc():
     """slicer::GlibcRand (private state) == libc srand/rand, which the reference uses (densitymaps.cpp:187-223, :393)."""
     from oracle.oracle_bindings import libc_rand, libc_srand
