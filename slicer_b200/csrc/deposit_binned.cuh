@@ -46,6 +46,11 @@ struct EmitDev
   unsigned *region_count;   // [regions]
   unsigned long long region_cap;
   int ntile;                // tiles per map side
+  // Maps with more (plane, tile) pairs than one sort handles (8192^2: 4 x 2500) sort by GROUPS of 2^gshift tiles adjacent in x:
+  // a bin then holds the records of the whole group, and the tile kernel runs one CTA per tile that skips its neighbours' records
+  // (a second read of an 8-byte record is far cheaper than a second sort window over all records).
+  int ntx;                  // tile groups per map row: ceil(ntile / 2^gshift)
+  int gshift;
 };
 
 struct SortDev
@@ -66,11 +71,11 @@ struct SortDev
   unsigned long long capacity; // records rec_u/rec_s/key_u can hold (bounds checks of the checked build)
 };
 
-__device__ __forceinline__ int bin_of(int q, int gx, int gy, int nn, int ntile)
+__device__ __forceinline__ int bin_of(int q, int gx, int gy, int nn, int ntile, int ntx, int gshift)
 {
   const int cx = min(max(gx, 0), nn - 1) / TILE;
   const int cy = min(max(gy, 0), nn - 1) / TILE;
-  return (q * ntile + cy) * ntile + cx;
+  return (q * ntile + cy) * ntx + (cx >> gshift);
 }
 
 // keys of a region, four at a time (region offsets are multiples of 1024 records, so the 8-byte loads are aligned)
@@ -366,21 +371,28 @@ static inline void launch_bin_scatter(const SortDev &Q, bool windowed, cudaStrea
 // K3: one CTA per (plane, tile) bin
 template <int MAS>
 __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
-    tile_deposit_kernel(const __grid_constant__ PassParams P, const __grid_constant__ SortDev D, int ntile, int type, float const_mass)
+    tile_deposit_kernel(const __grid_constant__ PassParams P, const __grid_constant__ SortDev D, int ntile, int ntx, int gshift, int type,
+                        float const_mass)
 {
   extern __shared__ __align__(16) unsigned tile_smem[];
-  __shared__ unsigned s_ingrid;
+  __shared__ unsigned s_ingrid, s_n;
   unsigned *lo = tile_smem;
   unsigned *hi = tile_smem + TCELLS;
-  const unsigned r0 = D.bin_start[blockIdx.x], r1 = D.bin_start[blockIdx.x + 1];
+  const int bl = blockIdx.x >> gshift, sub = blockIdx.x & ((1 << gshift) - 1); // bin of this launch, tile within the bin's group
+  const unsigned r0 = D.bin_start[bl], r1 = D.bin_start[bl + 1];
   if (r0 == r1)
     return;
   if (threadIdx.x == 0)
+  {
     s_ingrid = 0;
-  const int b = blockIdx.x + D.bin_lo;
-  const int q = b / (ntile * ntile);
-  const int tb = b - q * ntile * ntile;
-  const int ty = tb / ntile, tx = tb - ty * ntile;
+    s_n = 0;
+  }
+  const int b = bl + D.bin_lo;
+  const int q = b / (ntile * ntx);
+  const int tb = b - q * ntile * ntx;
+  const int ty = tb / ntx, tx = ((tb - ty * ntx) << gshift) + sub;
+  if (tx >= ntile)
+    return; // the last group of a row may be incomplete
   const PlaneDev &L = P.pl[q];
   const int nn = L.npix;
   const int x0 = tx * TILE - 1, y0 = ty * TILE - 1; // map cell of local (0,0)
@@ -388,7 +400,7 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
   // path (densitymaps.cpp:402-403), the record kernel does not count.  Only a border tile can hold records whose nearest
   // grid point is outside the map.
   const bool border = tx == 0 || ty == 0 || tx == ntile - 1 || ty == ntile - 1;
-  unsigned my_ingrid = 0;
+  unsigned my_ingrid = 0, my_n = 0; // (my_n: records of THIS tile when the bin holds a group of tiles)
   for (int i = threadIdx.x; i < 2 * TCELLS; i += DEPOSIT_THREADS)
     tile_smem[i] = 0;
   __syncthreads();
@@ -398,6 +410,12 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
   auto one = [&](float xs, float ys, float m, float sm) {
     const int gx = __float2int_rd(__fmul_rn(xs, L.npixf));
     const int gy = __float2int_rd(__fmul_rn(ys, L.npixf));
+    if (gshift)
+    { // the bin holds the records of 2^gshift tiles: this CTA deposits its own
+      if (min(max(gx, 0), nn - 1) / TILE != tx)
+        return;
+      my_n++;
+    }
     if (border)
       my_ingrid += (gx >= 0 && gx < nn && gy >= 0 && gy < nn) ? 1u : 0u;
     if constexpr (MAS == SLICER_MAS_NGP)
@@ -501,11 +519,18 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
     if ((threadIdx.x & 31) == 0 && wsum)
       atomicAdd(&s_ingrid, wsum);
   }
+  if (gshift)
+  {
+    const unsigned wsum = __reduce_add_sync(0xffffffffu, my_n);
+    if ((threadIdx.x & 31) == 0 && wsum)
+      atomicAdd(&s_n, wsum);
+  }
   __syncthreads();
   if (threadIdx.x == 0)
   {
-    atomicAdd(L.counts + 2 * type, (unsigned long long)(r1 - r0));
-    atomicAdd(L.counts + 2 * type + 1, (unsigned long long)(border ? s_ingrid : r1 - r0));
+    const unsigned mine = gshift ? s_n : r1 - r0;
+    atomicAdd(L.counts + 2 * type, (unsigned long long)mine);
+    atomicAdd(L.counts + 2 * type + 1, (unsigned long long)(border ? s_ingrid : mine));
   }
   unsigned long long *map = L.acc + L.type_stride * (unsigned long long)type;
   for (int i = threadIdx.x; i < TCELLS; i += DEPOSIT_THREADS)

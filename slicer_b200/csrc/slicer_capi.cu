@@ -863,6 +863,16 @@ static void fill_segment(const slicer_handle *h, const Segment &s, SegmentDev *D
 // binned deposit: K1 (records) -> histogram -> scan -> scatter -> tile deposit, slice by slice
 // ------------------------------------------------------------------------------------------------------------
 static int binned_tiles(const PassParams &P) { return (P.pl[0].npix + binned::TILE - 1) / binned::TILE; }
+// Sort bins = (plane, tile row, group of 2^gshift tiles along x).  Groups are as small as possible for the bins of the pass to
+// fit one sort (MAX_BINS); beyond groups of four tiles the sort runs in windows of the bins.
+static int binned_gshift(const PassParams &P)
+{
+  const int nt = binned_tiles(P);
+  int g = 0;
+  while (g < 2 && (long long)P.nplanes * nt * ((nt + (1 << g) - 1) >> g) > binned::MAX_BINS)
+    g++;
+  return g;
+}
 
 // 0: direct map atomics; 1: binned.  When the planes' tiles exceed MAX_BINS (8192^2 maps) the records are still
 // produced once; the sort and the tile deposit then run window by window over the bins (binned_pass).
@@ -873,9 +883,9 @@ static int use_binned(const slicer_handle *h, const PassParams &P, const Segment
   for (int q = 1; q < P.nplanes; q++)
     if (P.pl[q].npix != P.pl[0].npix)
       return 0;
-  const int nt = binned_tiles(P);
-  if ((long long)P.nplanes * nt * nt > 65536)
-    return 0; // record keys are 16 bits (16 planes of 10624^2 pixels still fit)
+  const int nt = binned_tiles(P), gs = binned_gshift(P);
+  if ((long long)P.nplanes * nt * ((nt + (1 << gs) - 1) >> gs) > 65536)
+    return 0; // record keys are 16 bits (16 planes of 21248^2 pixels still fit)
   if (h->cfg.deposit_mode == SLICER_DEPOSIT_BINNED)
     return 1;
   // the sort + tile kernels cost ~65 us per segment before the first record; a record then costs ~50 ps against ~105 ps of
@@ -923,13 +933,14 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
 {
   if (binned_alloc(h, D.mass != nullptr))
     return 1;
-  const int nt = binned_tiles(P);
-  const int nbins = P.nplanes * nt * nt;
+  const int nt = binned_tiles(P), gshift = binned_gshift(P), ntx = (nt + (1 << gshift) - 1) >> gshift;
+  const int nbins = P.nplanes * nt * ntx;
   // few accepted particles: one slice as large as the buffers allow (the per-slice fixed costs dominate);
   // many: 2^28-particle slices (measured optimum at 25-55 % acceptance)
   size_t slice = h->bin.slice;
   // (not for maps of several bin windows: their tiles are sparsely filled, the per-tile zero + flush dominates)
-  if (P.est_accept >= 0.12 && nbins <= binned::MAX_BINS && slice > ((size_t)1 << 28))
+  // (not for maps of thousands of tiles: their tiles are sparsely filled, the per-tile zero + flush and the per-sort set-up dominate)
+  if (P.est_accept >= 0.12 && (long long)P.nplanes * nt * nt <= 1024 && slice > ((size_t)1 << 28))
     slice = (size_t)1 << 28;
   // a particle yields up to one record per randomisation of the pass: the slice shrinks so that the regions still fit
   if (P.nxform > 1)
@@ -954,6 +965,8 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
     E.region_count = h->bin.region_count;
     E.region_cap = cmax * pipe::CHUNK * (unsigned long long)P.nxform; // one region per K1 CTA: every (particle, randomisation) pair of its chunks could be accepted
     E.ntile = nt;
+    E.ntx = ntx;
+    E.gshift = gshift;
     const int nregions = grid;
     if ((unsigned long long)nregions * E.region_cap > h->bin.capacity)
       return fail("binned deposit: record buffer too small (internal error)");
@@ -987,9 +1000,9 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
       if (!(h->debug & 4)) // measurement aid: SLICER_B200_DEBUG bit 2 skips the tile deposit
       {
         if (h->cfg.mas == SLICER_MAS_NGP)
-          binned::tile_deposit_kernel<SLICER_MAS_NGP><<<Q.nbins, binned::DEPOSIT_THREADS, binned::TCELLS * 8, h->compute>>>(P, Q, nt, D.type, D.const_mass);
+          binned::tile_deposit_kernel<SLICER_MAS_NGP><<<Q.nbins << gshift, binned::DEPOSIT_THREADS, binned::TCELLS * 8, h->compute>>>(P, Q, nt, ntx, gshift, D.type, D.const_mass);
         else
-          binned::tile_deposit_kernel<SLICER_MAS_TSC><<<Q.nbins, binned::DEPOSIT_THREADS, binned::TCELLS * 8, h->compute>>>(P, Q, nt, D.type, D.const_mass);
+          binned::tile_deposit_kernel<SLICER_MAS_TSC><<<Q.nbins << gshift, binned::DEPOSIT_THREADS, binned::TCELLS * 8, h->compute>>>(P, Q, nt, ntx, gshift, D.type, D.const_mass);
       }
       h->stats.launches += 4;
     }
