@@ -6,30 +6,48 @@
 // int64 fixed point -> float32 map, summing `ntypes` per-type accumulators first (exact integer sum).
 // Replaces the float adds of densitymaps.cpp:511-513 and the float MPI_Reduce of slicer-v2.cpp:214-217:
 // one rounding per pixel instead of one per particle.
+// Masses are non-negative, so an accumulator (or a sum over types) with the sign bit set has run past 2^63 — 8.4e6 mass units per
+// pixel at the default 40 fraction bits: `overflow` is raised and the read-out fails instead of returning a wrapped map.
 __global__ void finalize_map_kernel(const unsigned long long *__restrict__ acc, unsigned long long type_stride, int ntypes,
-                                    unsigned long long npix2, double inv_scale, float *__restrict__ out)
+                                    unsigned long long npix2, double inv_scale, float *__restrict__ out, unsigned *__restrict__ overflow)
 {
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  bool bad = false;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix2; i += stride)
   {
     long long s = 0;
     for (int t = 0; t < ntypes; t++)
-      s += (long long)acc[(unsigned long long)t * type_stride + i];
+    {
+      const long long a = (long long)acc[(unsigned long long)t * type_stride + i];
+      bad = bad || a < 0;
+      s += a;
+    }
+    bad = bad || s < 0;
     out[i] = __double2float_rn(__dmul_rn((double)s, inv_scale));
   }
+  if (bad)
+    atomicOr(overflow, 1u);
 }
 
 __global__ void sum_types_kernel(const unsigned long long *__restrict__ acc, unsigned long long type_stride, int ntypes,
-                                 unsigned long long npix2, long long *__restrict__ out)
+                                 unsigned long long npix2, long long *__restrict__ out, unsigned *__restrict__ overflow)
 {
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  bool bad = false;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < npix2; i += stride)
   {
     long long s = 0;
     for (int t = 0; t < ntypes; t++)
-      s += (long long)acc[(unsigned long long)t * type_stride + i];
+    {
+      const long long a = (long long)acc[(unsigned long long)t * type_stride + i];
+      bad = bad || a < 0;
+      s += a;
+    }
+    bad = bad || s < 0;
     out[i] = s;
   }
+  if (bad)
+    atomicOr(overflow, 1u);
 }
 
 // Counter-based generator: 24-bit uniform from splitmix64(seed, 3*i+k), scaled by the box (float multiply).

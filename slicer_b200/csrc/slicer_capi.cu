@@ -342,7 +342,7 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
     if (cfg->mass_capacity && (rc = dev_alloc(h, &h->d_mass_pool, h->nbuf * h->mass_stride)))
       break;
     h->defer.cap = 1u << 20;
-    if ((rc = dev_alloc(h, &h->defer.buf, (size_t)h->defer.cap)) || (rc = dev_alloc(h, &h->defer.count, 1)))
+    if ((rc = dev_alloc(h, &h->defer.buf, (size_t)h->defer.cap)) || (rc = dev_alloc(h, &h->defer.count, 2))) // [1]: accumulator overflow flag
       break;
     if (cudaHostAlloc((void **)&h->defer.host, (size_t)h->defer.cap * sizeof(DeferEntry), cudaHostAllocDefault) != cudaSuccess)
     {
@@ -368,7 +368,7 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
     }
     if (cudaMemsetAsync(h->d_acc, 0, (size_t)cfg->max_planes * h->ntypes_alloc * h->npix2max * 8, h->compute) != cudaSuccess ||
         cudaMemsetAsync(h->d_counts, 0, (size_t)SLICER_MAX_PLANES * SLICER_NTYPES * 2 * 8, h->compute) != cudaSuccess ||
-        cudaMemsetAsync(h->defer.count, 0, sizeof(unsigned), h->compute) != cudaSuccess ||
+        cudaMemsetAsync(h->defer.count, 0, 2 * sizeof(unsigned), h->compute) != cudaSuccess ||
         cudaStreamSynchronize(h->compute) != cudaSuccess)
     {
       rc = fail("initial memset failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1530,11 +1530,13 @@ extern "C" int slicer_fetch(slicer_handle *h, int plane, int type, float *out_ma
     const unsigned long long *src = type >= 0 ? base + (size_t)type * h->npix2max : base;
     const int nt = type >= 0 ? 1 : h->ntypes_alloc;
     const int blocks = (int)((npix2 + 255) / 256 < (size_t)h->sm_count * 8 ? (npix2 + 255) / 256 : (size_t)h->sm_count * 8);
-    finalize_map_kernel<<<blocks, 256, 0, h->compute>>>(src, h->npix2max, nt, npix2, ldexp(1.0, -h->frac_bits), h->d_out);
+    finalize_map_kernel<<<blocks, 256, 0, h->compute>>>(src, h->npix2max, nt, npix2, ldexp(1.0, -h->frac_bits), h->d_out, h->defer.count + 1);
     CU(cudaGetLastError());
     h->stats.launches++;
     CU(cudaMemcpyAsync(out_map, h->d_out, npix2 * sizeof(float), cudaMemcpyDeviceToHost, h->compute));
   }
+  unsigned ovf = 0;
+  CU(cudaMemcpyAsync(&ovf, h->defer.count + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, h->compute));
   unsigned long long c[SLICER_NTYPES * 2];
   CU(cudaMemcpyAsync(c, h->d_counts + (size_t)plane * SLICER_NTYPES * 2, sizeof(c), cudaMemcpyDeviceToHost, h->compute));
   CU(cudaStreamSynchronize(h->compute));
@@ -1544,6 +1546,12 @@ extern "C" int slicer_fetch(slicer_handle *h, int plane, int type, float *out_ma
       counts[t] = (long long)c[2 * t];
     if (ingrid)
       ingrid[t] = (long long)c[2 * t + 1];
+  }
+  if (ovf)
+  {
+    CU(cudaMemsetAsync(h->defer.count + 1, 0, sizeof(unsigned), h->compute));
+    return fail("plane %d: a fixed-point accumulator exceeded 2^63 (more than %.3g mass units in one pixel at %d fraction bits); "
+                "create the handle with a smaller slicer_config.frac_bits", plane, ldexp(1.0, 63 - h->frac_bits), h->frac_bits);
   }
   return 0;
 }
@@ -1559,11 +1567,19 @@ extern "C" int slicer_fetch_fixed(slicer_handle *h, int plane, int type, long lo
   const unsigned long long *src = type >= 0 ? base + (size_t)type * h->npix2max : base;
   const int nt = type >= 0 ? 1 : h->ntypes_alloc;
   const int blocks = (int)((npix2 + 255) / 256 < (size_t)h->sm_count * 8 ? (npix2 + 255) / 256 : (size_t)h->sm_count * 8);
-  sum_types_kernel<<<blocks, 256, 0, h->compute>>>(src, h->npix2max, nt, npix2, h->d_sum);
+  sum_types_kernel<<<blocks, 256, 0, h->compute>>>(src, h->npix2max, nt, npix2, h->d_sum, h->defer.count + 1);
   CU(cudaGetLastError());
   h->stats.launches++;
   CU(cudaMemcpyAsync(out, h->d_sum, npix2 * sizeof(long long), cudaMemcpyDeviceToHost, h->compute));
+  unsigned ovf = 0;
+  CU(cudaMemcpyAsync(&ovf, h->defer.count + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, h->compute));
   CU(cudaStreamSynchronize(h->compute));
+  if (ovf)
+  {
+    CU(cudaMemsetAsync(h->defer.count + 1, 0, sizeof(unsigned), h->compute));
+    return fail("plane %d: a fixed-point accumulator exceeded 2^63 (more than %.3g mass units in one pixel at %d fraction bits); "
+                "create the handle with a smaller slicer_config.frac_bits", plane, ldexp(1.0, 63 - h->frac_bits), h->frac_bits);
+  }
   return 0;
 }
 

@@ -741,3 +741,26 @@ def test_rounding_guard_of_the_general_chain(oracle, kernel):
         assert np.array_equal(fixed, res["fixed"][1])
         if eta:
             assert flagged > 5_000
+
+
+def test_accumulator_overflow_is_reported():
+    """int64 fixed point holds 2^(63 - frac_bits) mass units per pixel (8.4e6 at the default 40 bits).  A pixel that runs past that
+    is detected at read-out (the sign bit of a sum of non-negative masses) and the fetch fails instead of returning a wrapped map
+    (ADVICE r1)."""
+    box = 128000.0
+    n = 48
+    pos = np.tile(np.array([[0.5, 0.5, 0.3]], np.float32) * np.float32(box), (n, 1))  # every particle into the same pixel
+    d = capi.plane_desc([1, 1, 1], 1, [0.0, 0.0, 0.0], 0.0, 10.0, 100.0, 0.5, 64)
+    with capi.Slicer(npix_max=64, max_planes=1, mas=capi.MAS_NGP, particle_capacity=n + 64, frac_bits=58) as s:
+        s.begin_snapshot(box, [0, 1.0, 0, 0, 0, 0], False)
+        s.stage(1, pos)
+        s.deposit([d])  # 48 particles x 2^58 = 1.4e19: past 2^63, short of 2^64
+        with pytest.raises(capi.SlicerError, match="exceeded 2\\^63"):
+            s.fetch_fixed(0, -1, 64)
+        with pytest.raises(capi.SlicerError, match="frac_bits"):
+            s.fetch(0, -1, 64)
+    with capi.Slicer(npix_max=64, max_planes=1, mas=capi.MAS_NGP, particle_capacity=n + 64, frac_bits=40) as s:
+        s.begin_snapshot(box, [0, 1.0, 0, 0, 0, 0], False)
+        s.stage(1, pos)
+        s.deposit([d])
+        assert int(s.fetch_fixed(0, -1, 64).sum()) == n << 40
