@@ -207,54 +207,59 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
 // addresses.  No global atomics; the bin layout is deterministic up to the order inside a (batch, bin) run.
 constexpr int SCATTER_BATCH = 16384;
 constexpr int SCATTER_PER = SCATTER_BATCH / SCATTER_THREADS; // records per thread per batch
-// NB = table size: MAX_BINS, or SMALL_BINS for the usual few-plane 2048^2 passes (a shorter scan per batch)
+// NB = table size: MAX_BINS, or SMALL_BINS for the usual few-plane 2048^2 passes (a shorter scan per batch).
+// (Measured and not kept: two 768-thread CTAs per SM with 6 K-record batches and 1536-bin tables, to overlap the phases between
+// the barriers: 5.25 instead of 4.2 ms on the densest C3 group — the shorter runs cost more than the overlap gains.)
 constexpr int SMALL_BINS = 4096;
-template <int NB>
+template <int NB, int THREADS, int PER>
 struct ScatterSmem
 {
-  float2 rec[SCATTER_BATCH];
-  unsigned short bin[SCATTER_BATCH];
+  float2 rec[THREADS * PER];
+  unsigned short bin[THREADS * PER];
   unsigned cnt[NB];    // records of the batch per bin, then running rank
   unsigned lstart[NB]; // first sorted slot of the bin in this batch
   unsigned gcur[NB];   // next free global slot of the bin for this region
-  unsigned wsum[SCATTER_THREADS / 32];
+  unsigned wsum[THREADS / 32];
   unsigned ntot; // records of the batch inside the bin window
 };
 
 // WIN: the sort covers a window of the bins only (maps with more than MAX_BINS plane-tiles), other records are skipped
-template <int NB, bool WIN>
-__global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const __grid_constant__ SortDev D)
+template <int NB, bool WIN, int THREADS, int PER, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS) bin_scatter_kernel(const __grid_constant__ SortDev D)
 {
   extern __shared__ __align__(16) unsigned char scatter_raw[];
-  ScatterSmem<NB> &sm = *reinterpret_cast<ScatterSmem<NB> *>(scatter_raw);
+  using Sm = ScatterSmem<NB, THREADS, PER>;
+  Sm &sm = *reinterpret_cast<Sm *>(scatter_raw);
   float *smass = reinterpret_cast<float *>(sm.rec); // per-particle masses reuse the record staging in a second sweep
-  constexpr int PER = NB / SCATTER_THREADS; // bins per thread in the scan
+  constexpr int BATCH = THREADS * PER;
+  constexpr int PERB = NB / THREADS; // bins per thread in the scan
+  static_assert(NB % THREADS == 0 && THREADS % 32 == 0 && THREADS / 32 <= 32, "scan layout");
   const int r = blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const unsigned n = D.region_count[r];
   if (n == 0)
     return;
-  for (int i = t; i < D.nbins; i += SCATTER_THREADS)
+  for (int i = t; i < D.nbins; i += THREADS)
     sm.gcur[i] = D.bin_start[i] + D.region_hist[(size_t)i * D.nregions + r];
-  for (int i = D.nbins + t; i < NB; i += SCATTER_THREADS)
-    sm.cnt[i] = 0; // never incremented: the batch scan runs over all MAX_BINS entries
+  for (int i = D.nbins + t; i < NB; i += THREADS)
+    sm.cnt[i] = 0; // never incremented: the batch scan runs over all NB entries
   const unsigned long long off = (unsigned long long)r * D.region_cap;
   const unsigned short *key = D.key_u + off;
   const float2 *rec = D.rec_u + off;
   const float *mass = D.mass_u ? D.mass_u + off : nullptr;
-  for (unsigned base = 0; base < n; base += SCATTER_BATCH)
+  for (unsigned base = 0; base < n; base += BATCH)
   {
-    const unsigned nb = min(n - base, (unsigned)SCATTER_BATCH);
-    for (int i = t; i < D.nbins; i += SCATTER_THREADS)
+    const unsigned nb = min(n - base, (unsigned)BATCH);
+    for (int i = t; i < D.nbins; i += THREADS)
       sm.cnt[i] = 0;
     __syncthreads();
     // 1. coalesced loads, rank inside (batch, bin)
-    unsigned k[SCATTER_PER]; // bin | rank << 16 (rank < SCATTER_BATCH = 2^13)
-    float2 e[SCATTER_PER];
+    unsigned k[PER]; // bin | rank << 16 (rank < BATCH <= 2^14)
+    float2 e[PER];
 #pragma unroll
-    for (int j = 0; j < SCATTER_PER; j++)
+    for (int j = 0; j < PER; j++)
     {
-      const unsigned i = j * SCATTER_THREADS + t;
+      const unsigned i = j * THREADS + t;
       k[j] = 0xffffffffu;
       if (i < nb)
       {
@@ -265,16 +270,16 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
       }
     }
 #pragma unroll
-    for (int j = 0; j < SCATTER_PER; j++)
+    for (int j = 0; j < PER; j++)
       if (k[j] != 0xffffffffu)
         k[j] |= atomicAdd(&sm.cnt[k[j]], 1u) << 16;
     __syncthreads();
-    // 2. exclusive scan of the batch histogram: thread t owns bins [PER t, PER t + PER)
-    unsigned c[PER], x = 0;
+    // 2. exclusive scan of the batch histogram: thread t owns bins [PERB t, PERB t + PERB)
+    unsigned c[PERB], x = 0;
 #pragma unroll
-    for (int j = 0; j < PER; j++)
+    for (int j = 0; j < PERB; j++)
     {
-      c[j] = sm.cnt[PER * t + j];
+      c[j] = sm.cnt[PERB * t + j];
       x += c[j];
     }
     unsigned incl = x;
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
     __syncthreads();
     if (w == 0)
     {
-      const unsigned sv = lane < SCATTER_THREADS / 32 ? sm.wsum[lane] : 0u;
+      const unsigned sv = lane < THREADS / 32 ? sm.wsum[lane] : 0u;
       unsigned si = sv;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1)
@@ -299,34 +304,34 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
         if (lane >= d)
           si += y;
       }
-      if (lane < SCATTER_THREADS / 32)
+      if (lane < THREADS / 32)
         sm.wsum[lane] = si - sv;
     }
     __syncthreads();
     unsigned ex = sm.wsum[w] + incl - x;
 #pragma unroll
-    for (int j = 0; j < PER; j++)
+    for (int j = 0; j < PERB; j++)
     {
-      sm.lstart[PER * t + j] = ex;
+      sm.lstart[PERB * t + j] = ex;
       ex += c[j];
     }
-    if (WIN && t == SCATTER_THREADS - 1)
+    if (WIN && t == THREADS - 1)
       sm.ntot = ex;
     __syncthreads();
     const unsigned ntot = WIN ? sm.ntot : nb;
     // 3. sorted order in shared memory
 #pragma unroll
-    for (int j = 0; j < SCATTER_PER; j++)
+    for (int j = 0; j < PER; j++)
       if (k[j] != 0xffffffffu)
       {
         const unsigned lp = sm.lstart[k[j] & 0xffffu] + (k[j] >> 16);
-        SLICER_CHECK((k[j] & 0xffffu) < (unsigned)D.nbins && lp < (unsigned)SCATTER_BATCH);
+        SLICER_CHECK((k[j] & 0xffffu) < (unsigned)D.nbins && lp < (unsigned)BATCH);
         sm.rec[lp] = e[j];
         sm.bin[lp] = (unsigned short)(k[j] & 0xffffu);
       }
     __syncthreads();
     // 4. write-out: slot i of the sorted batch -> gcur[bin] + (i - lstart[bin]); runs are contiguous in memory
-    for (unsigned i = t; i < ntot; i += SCATTER_THREADS)
+    for (unsigned i = t; i < ntot; i += THREADS)
     {
       const unsigned b = sm.bin[i];
       const unsigned dst = sm.gcur[b] + (i - sm.lstart[b]);
@@ -337,11 +342,11 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
     if (mass)
     { // same permutation for the masses
 #pragma unroll
-      for (int j = 0; j < SCATTER_PER; j++)
+      for (int j = 0; j < PER; j++)
         if (k[j] != 0xffffffffu)
-          smass[sm.lstart[k[j] & 0xffffu] + (k[j] >> 16)] = mass[base + j * SCATTER_THREADS + t];
+          smass[sm.lstart[k[j] & 0xffffu] + (k[j] >> 16)] = mass[base + j * THREADS + t];
       __syncthreads();
-      for (unsigned i = t; i < ntot; i += SCATTER_THREADS)
+      for (unsigned i = t; i < ntot; i += THREADS)
       {
         const unsigned b = sm.bin[i];
         D.mass_s[sm.gcur[b] + (i - sm.lstart[b])] = smass[i];
@@ -349,23 +354,29 @@ __global__ void __launch_bounds__(SCATTER_THREADS, 1) bin_scatter_kernel(const _
       __syncthreads();
     }
 #pragma unroll
-    for (int j = 0; j < PER; j++)
-      sm.gcur[PER * t + j] += c[j];
+    for (int j = 0; j < PERB; j++)
+      sm.gcur[PERB * t + j] += c[j];
   }
 }
 
+using ScatterSmall = ScatterSmem<SMALL_BINS, SCATTER_THREADS, SCATTER_PER>;
+using ScatterWin = ScatterSmem<MAX_BINS, SCATTER_THREADS, SCATTER_PER>;
+
 static inline cudaError_t prepare_bin_scatter()
 {
-  cudaError_t e = cudaFuncSetAttribute(bin_scatter_kernel<SMALL_BINS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<SMALL_BINS>));
-  return e != cudaSuccess ? e : cudaFuncSetAttribute(bin_scatter_kernel<MAX_BINS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScatterSmem<MAX_BINS>));
+  cudaError_t e = cudaFuncSetAttribute(bin_scatter_kernel<SMALL_BINS, false, SCATTER_THREADS, SCATTER_PER, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(ScatterSmall));
+  return e != cudaSuccess ? e
+                          : cudaFuncSetAttribute(bin_scatter_kernel<MAX_BINS, true, SCATTER_THREADS, SCATTER_PER, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)sizeof(ScatterWin));
 }
 
 static inline void launch_bin_scatter(const SortDev &Q, bool windowed, cudaStream_t stream)
 {
   if (!windowed && Q.nbins <= SMALL_BINS)
-    bin_scatter_kernel<SMALL_BINS, false><<<Q.nregions, SCATTER_THREADS, sizeof(ScatterSmem<SMALL_BINS>), stream>>>(Q);
+    bin_scatter_kernel<SMALL_BINS, false, SCATTER_THREADS, SCATTER_PER, 1><<<Q.nregions, SCATTER_THREADS, sizeof(ScatterSmall), stream>>>(Q);
   else
-    bin_scatter_kernel<MAX_BINS, true><<<Q.nregions, SCATTER_THREADS, sizeof(ScatterSmem<MAX_BINS>), stream>>>(Q);
+    bin_scatter_kernel<MAX_BINS, true, SCATTER_THREADS, SCATTER_PER, 1><<<Q.nregions, SCATTER_THREADS, sizeof(ScatterWin), stream>>>(Q);
 }
 
 // K3: one CTA per (plane, tile) bin
