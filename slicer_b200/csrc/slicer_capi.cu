@@ -120,6 +120,9 @@ struct slicer_handle
   size_t npix2max;
   int sm_count;
   cudaStream_t compute = nullptr, copy = nullptr, comm_stream = nullptr;
+  cudaStream_t aux = nullptr;                      // zeroing of large accumulators, concurrent with the record kernel of a binned pass
+  cudaEvent_t ev_zero_start = nullptr, ev_zero_done = nullptr;
+  bool zero_pending = false;                       // the compute stream has not yet waited for ev_zero_done
   cudaEvent_t ev_pass_done = nullptr;              // compute -> comm_stream: the passes a reduce sums
   cudaEvent_t ev_slot[SLICER_MAX_PLANES];          // comm_stream -> compute: the last reduce of accumulator slot q
   bool slot_reducing[SLICER_MAX_PLANES];           // ev_slot[q] is pending
@@ -309,6 +312,9 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
     TRY(cudaStreamCreateWithFlags(&h->compute, cudaStreamNonBlocking));
     TRY(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
     TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    TRY(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+    TRY(cudaEventCreateWithFlags(&h->ev_zero_start, cudaEventDisableTiming));
+    TRY(cudaEventCreateWithFlags(&h->ev_zero_done, cudaEventDisableTiming));
     TRY(cudaEventCreateWithFlags(&h->ev_pass_done, cudaEventDisableTiming));
     for (int q = 0; q < SLICER_MAX_PLANES; q++)
       TRY(cudaEventCreateWithFlags(&h->ev_slot[q], cudaEventDisableTiming));
@@ -436,6 +442,15 @@ extern "C" void slicer_destroy(slicer_handle *h)
   for (size_t i = 0; i < h->pass_ev.size(); i++)
     if (h->pass_ev[i])
       cudaEventDestroy(h->pass_ev[i]);
+  if (h->aux)
+  {
+    cudaStreamSynchronize(h->aux);
+    cudaStreamDestroy(h->aux);
+  }
+  if (h->ev_zero_start)
+    cudaEventDestroy(h->ev_zero_start);
+  if (h->ev_zero_done)
+    cudaEventDestroy(h->ev_zero_done);
   if (h->ev_pass_done)
     cudaEventDestroy(h->ev_pass_done);
   for (int q = 0; q < SLICER_MAX_PLANES; q++)
@@ -929,6 +944,18 @@ static int binned_alloc(slicer_handle *h, bool need_mass)
   return 0;
 }
 
+// Large accumulators are zeroed on a side stream (run_pass) so that the write overlaps the record kernel of a binned pass, which
+// does not touch the maps; whatever does touch them calls this first.
+static int maps_ready(slicer_handle *h)
+{
+  if (h->zero_pending)
+  {
+    CU(cudaStreamWaitEvent(h->compute, h->ev_zero_done, 0));
+    h->zero_pending = false;
+  }
+  return 0;
+}
+
 static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &D, const DeferDev &F)
 {
   if (binned_alloc(h, D.mass != nullptr))
@@ -997,6 +1024,8 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
       binned::bin_region_scan_kernel<<<Q.nbins, 1024, 0, h->compute>>>(Q);
       binned::bin_scan_kernel<<<1, 1024, 0, h->compute>>>(Q);
       binned::launch_bin_scatter(Q, nwin > 1, h->compute);
+      if (maps_ready(h))
+        return 1;
       if (!(h->debug & 4)) // measurement aid: SLICER_B200_DEBUG bit 2 skips the tile deposit
       {
         if (h->cfg.mas == SLICER_MAS_NGP)
@@ -1187,8 +1216,20 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
     return 1;
   if (!accumulate)
   {
-    CU(cudaMemsetAsync(h->d_acc + (size_t)first_slot * h->ntypes_alloc * h->npix2max, 0,
-                       (size_t)nplanes * h->ntypes_alloc * h->npix2max * sizeof(unsigned long long), h->compute));
+    const size_t zbytes = (size_t)nplanes * h->ntypes_alloc * h->npix2max * sizeof(unsigned long long);
+    unsigned long long *zptr = h->d_acc + (size_t)first_slot * h->ntypes_alloc * h->npix2max;
+    if (zbytes >= ((size_t)64 << 20))
+    { // (8192^2 planes: 2 GiB per pass, 0.7 ms on the compute stream) after everything queued so far, beside what comes next
+      if (maps_ready(h))
+        return 1;
+      CU(cudaEventRecord(h->ev_zero_start, h->compute));
+      CU(cudaStreamWaitEvent(h->aux, h->ev_zero_start, 0));
+      CU(cudaMemsetAsync(zptr, 0, zbytes, h->aux));
+      CU(cudaEventRecord(h->ev_zero_done, h->aux));
+      h->zero_pending = true;
+    }
+    else
+      CU(cudaMemsetAsync(zptr, 0, zbytes, h->compute));
     CU(cudaMemsetAsync(h->d_counts + (size_t)first_slot * SLICER_NTYPES * 2, 0, (size_t)nplanes * SLICER_NTYPES * 2 * sizeof(unsigned long long),
                        h->compute));
     for (int q = first_slot; q < first_slot + nplanes; q++)
@@ -1227,7 +1268,7 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
         if (binned_pass(h, P, D, F))
           return 1;
       }
-      else if (pipelined_launch(&h->pipe, h->cfg.mas, P, D, F, h->compute))
+      else if (maps_ready(h) || pipelined_launch(&h->pipe, h->cfg.mas, P, D, F, h->compute))
         return fail("pipelined launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     else
@@ -1235,6 +1276,8 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
       size_t want = (D.n + 255) / 256;
       size_t cap = (size_t)h->sm_count * 8;
       int blocks = (int)(want < cap ? want : cap);
+      if (maps_ready(h))
+        return 1;
       if (h->cfg.mas == SLICER_MAS_NGP)
         deposit_simple_kernel<SLICER_MAS_NGP><<<blocks, 256, 0, h->compute>>>(P, D, F);
       else
@@ -1245,6 +1288,8 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
     h->stats.deposit_launches++;
     h->stats.particles_streamed += D.n;
   }
+  if (maps_ready(h)) // (a pass without particles still leaves zeroed planes behind it in stream order)
+    return 1;
   CU(cudaEventRecord(e1, h->compute));
   CU(cudaEventRecord(h->ev_buf_done[h->cur_buf], h->compute));
   h->pass_head++;
