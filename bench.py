@@ -249,7 +249,8 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        "config": workload_config(args.workload, args.scaling, args.gpus) | {"sample": f"{ncores} sub-files x {n_per_core} particles per step"},
+        "config": workload_config(args.workload, args.scaling, args.gpus),  # identical to our arm's; the sample is described in cpu_baseline
+        "sample": f"{ncores} sub-files x {n_per_core} particles through the whole light cone per step",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ncores, "kind": "reference",
                          "sample": f"{ncores} processes (one per host core, as MPI ranks over sub-files), each createDensityMaps on a "
                                    f"{n_per_core}-particle sub-file for all {LENS_PER_SNAP * len(allg)} planes of the light cone per step"},
