@@ -167,6 +167,7 @@ struct slicer_handle
     DeferEntry *buf = nullptr;
     unsigned *count = nullptr;
     DeferEntry *host = nullptr; // pinned mirror
+    unsigned *host_count = nullptr; // pinned: the counter as of the end of the last pass (copied behind every pass)
     unsigned cap = 0;
     std::vector<SavedPass> passes; // passes since the last resolve; DeferEntry::pass indexes it
     bool failed = false;
@@ -355,6 +356,12 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
       rc = fail("cudaHostAlloc failed: %s", cudaGetErrorString(cudaGetLastError()));
       break;
     }
+    if (cudaHostAlloc((void **)&h->defer.host_count, 2 * sizeof(unsigned), cudaHostAllocDefault) != cudaSuccess)
+    {
+      rc = fail("cudaHostAlloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    h->defer.host_count[0] = 0;
     memset(h->slot_epoch, 0, sizeof(h->slot_epoch));
     h->d_pos = h->d_pos_pool;
     h->d_mass = h->d_mass_pool;
@@ -424,6 +431,8 @@ extern "C" void slicer_destroy(slicer_handle *h)
   cudaFree(h->defer.count);
   if (h->defer.host)
     cudaFreeHost(h->defer.host);
+  if (h->defer.host_count)
+    cudaFreeHost(h->defer.host_count);
   cudaFree(h->d_pos_pool);
   cudaFree(h->d_mass_pool);
   cudaFree(h->d_acc);
@@ -1063,6 +1072,8 @@ static int resolve_passes(slicer_handle *h, size_t n)
 // ------------------------------------------------------------------------------------------------------------
 // deferred particles of the lean exact phase (lean_math.h): the reference's own arithmetic with this host's libm
 // ------------------------------------------------------------------------------------------------------------
+static const unsigned DEFER_HEAD = 16384; // entries copied to the host behind every pass
+
 struct ResolvedRec
 {
   float xs, ys, m;
@@ -1114,22 +1125,28 @@ static int resolve_deferred(slicer_handle *h)
     return 0;
   if (set_device(h))
     return 1;
-  unsigned n = 0;
-  CU(cudaMemcpyAsync(&n, h->defer.count, sizeof(unsigned), cudaMemcpyDeviceToHost, h->compute));
+  // run_pass copies the counter and the head of the list to pinned memory behind every pass: one synchronisation settles the
+  // usual case (a few thousand entries), without further round trips
   CU(cudaStreamSynchronize(h->compute));
+  const unsigned n = h->defer.host_count[0];
   if (n > h->defer.cap)
   {
     h->defer.failed = true;
     h->defer.passes.clear();
     CU(cudaMemsetAsync(h->defer.count, 0, sizeof(unsigned), h->compute));
+    h->defer.host_count[0] = 0;
     return fail("%u particles within the rounding guard of a decision boundary exceed the deferred buffer (%u): the planes deposited since the "
                 "last fetch are incomplete; deposit and fetch in smaller batches",
                 n, h->defer.cap);
   }
   if (n)
   {
-    CU(cudaMemcpyAsync(h->defer.host, h->defer.buf, (size_t)n * sizeof(DeferEntry), cudaMemcpyDeviceToHost, h->compute));
-    CU(cudaStreamSynchronize(h->compute));
+    if (n > DEFER_HEAD)
+    {
+      CU(cudaMemcpyAsync(h->defer.host + DEFER_HEAD, h->defer.buf + DEFER_HEAD, (size_t)(n - DEFER_HEAD) * sizeof(DeferEntry), cudaMemcpyDeviceToHost,
+                         h->compute));
+      CU(cudaStreamSynchronize(h->compute));
+    }
     const size_t np = h->defer.passes.size();
     std::vector<std::vector<ResolvedRec>> out(np);
     for (unsigned i = 0; i < n; i++)
@@ -1172,7 +1189,8 @@ static int resolve_deferred(slicer_handle *h)
       off += m;
     }
     CU(cudaMemsetAsync(h->defer.count, 0, sizeof(unsigned), h->compute));
-    CU(cudaStreamSynchronize(h->compute)); // the pinned mirror is reused by the next call
+    h->defer.host_count[0] = 0;
+    // (no synchronisation here: the next call synchronises the stream before it touches the pinned mirror again)
   }
   h->defer.passes.clear();
   return 0;
@@ -1291,6 +1309,9 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
   if (maps_ready(h)) // (a pass without particles still leaves zeroed planes behind it in stream order)
     return 1;
   CU(cudaEventRecord(e1, h->compute));
+  // the deferred list as of now, for resolve_deferred
+  CU(cudaMemcpyAsync(h->defer.host_count, h->defer.count, sizeof(unsigned), cudaMemcpyDeviceToHost, h->compute));
+  CU(cudaMemcpyAsync(h->defer.host, h->defer.buf, (size_t)DEFER_HEAD * sizeof(DeferEntry), cudaMemcpyDeviceToHost, h->compute));
   CU(cudaEventRecord(h->ev_buf_done[h->cur_buf], h->compute));
   h->pass_head++;
   return 0;
