@@ -32,5 +32,5 @@ for g in groups:
 cudart.cudaProfilerStop()
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump({"workload": name, "groups": groups, "accepted_pairs": acc, "particles": wl.n, "bytes_per_pass": wl.bytes_per_pass, "csrc_sha": bench.csrc_sha()},
-          open(os.path.join(ROOT, "gpurun_out", f"r02_profile_meta_{name}.json"), "w"))
+          open(os.path.join(ROOT, "gpurun_out", f"r02_profile_meta_{name}{'_partial' if 'PGROUPS' in os.environ else ''}.json"), "w"))
 print("profiled groups", groups, "accepted", acc)
