@@ -40,8 +40,10 @@ static int make_handles(Engine *e)
     slicer_destroy(hh);
   e->h.assign(e->devices.size(), nullptr);
   e->comm = false;
-  for (size_t g = 0; g < e->devices.size(); g++)
-  {
+  // one thread per GPU: creating a CUDA context, loading the kernels and allocating the pools takes ~2 s per device, serially
+  // that was most of an 8-GPU run's wall clock
+  std::vector<std::string> errs(e->devices.size());
+  auto make_one = [&](size_t g) {
     slicer_config cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.device = e->devices[g];
@@ -56,11 +58,24 @@ static int make_handles(Engine *e)
     cfg.staging_buffers = 2;
     cfg.deposit_mode = e->deposit_mode;
     if (slicer_create(&cfg, &e->h[g]))
+      errs[g] = slicer_last_error(); // (thread-local: read it on the thread that made the call)
+  };
+  if (e->devices.size() == 1)
+    make_one(0);
+  else
+  {
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < e->devices.size(); g++)
+      th.emplace_back(make_one, g);
+    for (auto &t : th)
+      t.join();
+  }
+  for (size_t g = 0; g < e->devices.size(); g++)
+    if (!e->h[g])
     {
-      std::cerr << "slicer_create failed: " << slicer_last_error() << std::endl;
+      std::cerr << "slicer_create failed on GPU " << e->devices[g] << ": " << errs[g] << std::endl;
       return 1;
     }
-  }
   if (e->h.size() > 1)
   {
     if (slicer_comm_init_all(e->h.data(), (int)e->h.size()))
