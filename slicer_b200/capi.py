@@ -305,8 +305,8 @@ class Slicer:
         _check(lib().slicer_reduce_slots(self.h, int(first_slot), int(nplanes), int(root)))
 
     def selftest_arith(self, n: int, seed: int):
-        """(double division, double square root, float raw/box division of the lean box transform): how many results of the
-        guard-free forms differ from the IEEE library versions."""
+        """(reserved, reserved, mismatches): how many float quotients raw / box of the lean box transform's unchecked division differ
+        from __fdiv_rn."""
         out = (C.c_ulonglong * 3)()
         _check(lib().slicer_selftest_arith(self.h, int(n), int(seed), out))
         return tuple(int(v) for v in out)

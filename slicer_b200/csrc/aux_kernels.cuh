@@ -89,36 +89,12 @@ __global__ void synth_positions_kernel(float *__restrict__ pos, unsigned long lo
 }
 
 
-// ---- arithmetic self-check (chain::ddiv_fast, dsqrt_fast against the library's IEEE versions) ---------------------------
+// ---- arithmetic self-check -------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long selftest_mix(unsigned long long z)
 {
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
-}
-
-// n random operand pairs: a in +-[2^-300, 2^40), b in [2^-300, 2^40), x in [2^-600, 2^80) — far wider than what an accepted
-// particle produces (|a| in {0} u [2^-25, 8), b, x down to the square of the smallest float), inside the range where the
-// library itself takes its fast path (|a| >= 2^-967, normal quotient; x >= 2^-970).
-// out[0] += quotients that differ from __ddiv_rn, out[1] += roots that differ from __dsqrt_rn (bit comparison).
-__global__ void selftest_arith_kernel(unsigned long long n, unsigned long long seed, unsigned long long *out)
-{
-  unsigned long long bad_div = 0, bad_sqrt = 0;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-  {
-    const unsigned long long h1 = selftest_mix(seed + 3 * i), h2 = selftest_mix(seed + 3 * i + 1), h3 = selftest_mix(seed + 3 * i + 2);
-    // random mantissa, exponent drawn from the range, random sign for a
-    const double a = __longlong_as_double((long long)((h1 & 0x800fffffffffffffull) | ((unsigned long long)(1023 - 300 + (h1 >> 52) % 340) << 52)));
-    const double b = __longlong_as_double((long long)((h2 & 0x000fffffffffffffull) | ((unsigned long long)(1023 - 300 + (h2 >> 52) % 340) << 52)));
-    const double x = __longlong_as_double((long long)((h3 & 0x000fffffffffffffull) | ((unsigned long long)(1023 - 600 + (h3 >> 52) % 680) << 52)));
-    bad_div += __double_as_longlong(chain::ddiv_fast(a, b)) != __double_as_longlong(__ddiv_rn(a, b));
-    bad_sqrt += __double_as_longlong(chain::dsqrt_fast(x)) != __double_as_longlong(__dsqrt_rn(x));
-  }
-  if (bad_div)
-    atomicAdd(out, bad_div);
-  if (bad_sqrt)
-    atomicAdd(out + 1, bad_sqrt);
 }
 
 // The unchecked float division of the lean box transform (deposit_pipelined.cuh: lean_div_box) against __fdiv_rn:

@@ -851,7 +851,7 @@ static int build_pass(slicer_handle *h, const slicer_plane_desc *planes, int npl
   P->pair = P->fast && P->pl[0].nt > 0;
   for (int t = 0; t < P->nxform; t++)
     if (!P->xf[t].exact_f32)
-      P->pair = 0; // the pair paths assume a float-exact box and centre
+      P->pair = 0; // the lean exact phase assumes a float-exact box and centre
   for (int q = 1; q < P->nplanes; q++)
     if (P->pl[q].T != P->pl[0].T || P->pl[q].fovrad != P->pl[0].fovrad || P->pl[q].npix != P->pl[0].npix)
       P->pair = 0;
@@ -1328,7 +1328,6 @@ extern "C" int slicer_selftest_arith(slicer_handle *h, unsigned long long n, uns
     return fail("slicer_selftest_arith needs npix_max >= 3");
   CU(cudaStreamSynchronize(h->compute));
   CU(cudaMemset(d, 0, 3 * sizeof(unsigned long long)));
-  selftest_arith_kernel<<<h->sm_count * 8, 256, 0, h->compute>>>(n, seed, d);
   selftest_fdiv_kernel<<<h->sm_count * 8, 256, 0, h->compute>>>(n, seed, d);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->compute));

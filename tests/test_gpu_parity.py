@@ -557,10 +557,9 @@ def test_checked_build_traps_nothing():
 
 @pytest.mark.parametrize("seed", [1, 2, 3, 4])
 def test_guard_free_arithmetic_equals_ieee_library(seed):
-    """The exact phase uses guard-free forms of IEEE operations: the library's own fast paths without the range guard
-    (csrc/device_chain.cuh: ddiv_fast, dsqrt_fast; csrc/deposit_pipelined.cuh: lean_div_box = the float division raw / box of
-    gadget2io.cpp:204-206).  Bit-compare with __ddiv_rn / __dsqrt_rn / __fdiv_rn on 1e9 random operand pairs per seed, drawn
-    from the exponent ranges the paths admit."""
+    """The lean box transform divides raw / box (gadget2io.cpp:204-206) with the compiler's own IEEE fast path without its range
+    check (csrc/deposit_pipelined.cuh: lean_div_box; raw coordinates outside the admitted range take the general path).  Bit-compare
+    with __fdiv_rn on 1e9 random (raw, box) pairs per seed, drawn from the exponent ranges the path admits."""
     with capi.Slicer(npix_max=64, max_planes=1, mas=capi.MAS_TSC, particle_capacity=1024) as s:
         assert s.selftest_arith(1_000_000_000, 7919 * seed) == (0, 0, 0)
 
