@@ -199,6 +199,12 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(const __grid_constant__ 
     D.bin_start[D.nbins] = total;
 }
 
+// bulk prefetch of [p, p + bytes) into L2 (bytes a multiple of 16, p 16-byte aligned): one instruction, no registers, no wait
+__device__ __forceinline__ void l2_prefetch(const void *p, unsigned bytes)
+{
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // K2d: one CTA per region: record -> bin_start[bin] + (offset of this region in the bin) + (rank inside the region).
 // Measured on B200: a warp store whose 32 lanes hit 32 different sectors costs ~3-6 cycles per LANE per SM
 // (~50-100 G sector requests/s chip-wide, whatever the instruction: st, st.cs, red), 5x more than the same bytes
@@ -223,8 +229,17 @@ struct ScatterSmem
   unsigned ntot; // records of the batch inside the bin window
 };
 
-// WIN: the sort covers a window of the bins only (maps with more than MAX_BINS plane-tiles), other records are skipped
-template <int NB, bool WIN, int THREADS, int PER, int CTAS>
+// WIN: the sort covers a window of the bins only (maps with more than MAX_BINS plane-tiles), other records are skipped.
+// MASS: the records carry a per-particle mass (hydro segments): a second sweep applies the same permutation to the masses.
+//
+// Per batch of THREADS * PER records:  1. rank inside (batch, bin) by shared-memory atomics  2. exclusive scan of the batch
+// histogram  3. the records go to their sorted slot in shared memory  4. write-out in sorted order.  The global loads of a
+// batch are paired (one 16-byte load of two records, one 4-byte load of their two keys: half the load instructions in flight)
+// and the next batch is brought into L2 by a bulk prefetch (one instruction per array) while this one is sorted, so that its
+// loads do not wait for DRAM: 1.05 -> 0.83 ms per slice of the densest C3 group.  (Measured and not kept: loading the next
+// batch's keys into registers before the write-out — the register allocator spills them at 64 registers, which serialises
+// the loads: 1.18 ms; per-bin cursors in registers with one `slot -> global` offset table for the write-out: 1.0 ms.)
+template <int NB, bool WIN, bool MASS, int THREADS, int PER, int CTAS>
 __global__ void __launch_bounds__(THREADS, CTAS) bin_scatter_kernel(const __grid_constant__ SortDev D)
 {
   extern __shared__ __align__(16) unsigned char scatter_raw[];
@@ -233,20 +248,22 @@ __global__ void __launch_bounds__(THREADS, CTAS) bin_scatter_kernel(const __grid
   float *smass = reinterpret_cast<float *>(sm.rec); // per-particle masses reuse the record staging in a second sweep
   constexpr int BATCH = THREADS * PER;
   constexpr int PERB = NB / THREADS; // bins per thread in the scan
-  static_assert(NB % THREADS == 0 && THREADS % 32 == 0 && THREADS / 32 <= 32, "scan layout");
+  static_assert(NB % THREADS == 0 && THREADS % 32 == 0 && THREADS / 32 <= 32 && PER % 2 == 0, "scan layout");
   const int r = blockIdx.x;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const unsigned n = D.region_count[r];
   if (n == 0)
     return;
-  for (int i = t; i < D.nbins; i += THREADS)
-    sm.gcur[i] = D.bin_start[i] + D.region_hist[(size_t)i * D.nregions + r];
-  for (int i = D.nbins + t; i < NB; i += THREADS)
-    sm.cnt[i] = 0; // never incremented: the batch scan runs over all NB entries
+  for (int i = t; i < NB; i += THREADS)
+    sm.cnt[i] = 0; // (entries >= nbins are never incremented: the batch scan runs over all NB entries)
   const unsigned long long off = (unsigned long long)r * D.region_cap;
   const unsigned short *key = D.key_u + off;
   const float2 *rec = D.rec_u + off;
-  const float *mass = D.mass_u ? D.mass_u + off : nullptr;
+  const float *mass = MASS ? D.mass_u + off : nullptr;
+  // record j of the thread is record rec_index(j) of the batch
+  auto rec_index = [&](int j) { return 2u * (unsigned)((j >> 1) * THREADS + t) + (unsigned)(j & 1); };
+  for (int i = t; i < D.nbins; i += THREADS)
+    sm.gcur[i] = D.bin_start[i] + D.region_hist[(size_t)i * D.nregions + r];
   for (unsigned base = 0; base < n; base += BATCH)
   {
     const unsigned nb = min(n - base, (unsigned)BATCH);
@@ -256,18 +273,38 @@ __global__ void __launch_bounds__(THREADS, CTAS) bin_scatter_kernel(const __grid
     // 1. coalesced loads, rank inside (batch, bin)
     unsigned k[PER]; // bin | rank << 16 (rank < BATCH <= 2^14)
     float2 e[PER];
-#pragma unroll
-    for (int j = 0; j < PER; j++)
     {
-      const unsigned i = j * THREADS + t;
-      k[j] = 0xffffffffu;
-      if (i < nb)
+      // (region offsets and `base` are multiples of 1024 records: the paired loads are aligned)
+      const uint32_t *key2 = reinterpret_cast<const uint32_t *>(key + base);
+      const float4 *rec2 = reinterpret_cast<const float4 *>(rec + base);
+#pragma unroll
+      for (int jj = 0; jj < PER / 2; jj++)
       {
-        const unsigned kk = (unsigned)key[base + i] - (WIN ? (unsigned)D.bin_lo : 0u);
-        e[j] = rec[base + i]; // unconditionally: a load that waits for the key compare would serialise the two latencies
-        if (!WIN || kk < (unsigned)D.nbins)
-          k[j] = kk;
+        const unsigned pi = (unsigned)(jj * THREADS + t), i = 2u * pi;
+        k[2 * jj] = k[2 * jj + 1] = 0xffffffffu;
+        if (i < nb)
+        { // (the second record of the last pair of an odd batch is stale memory inside the region's capacity: loaded, ignored)
+          const uint32_t kk2 = key2[pi];
+          const float4 r4 = rec2[pi]; // unconditionally: a load that waits for the key compare would serialise the two latencies
+          e[2 * jj] = make_float2(r4.x, r4.y);
+          e[2 * jj + 1] = make_float2(r4.z, r4.w);
+          const unsigned k0 = (kk2 & 0xffffu) - (WIN ? (unsigned)D.bin_lo : 0u), k1 = (kk2 >> 16) - (WIN ? (unsigned)D.bin_lo : 0u);
+          if (!WIN || k0 < (unsigned)D.nbins)
+            k[2 * jj] = k0;
+          if ((!WIN || k1 < (unsigned)D.nbins) && i + 1 < nb)
+            k[2 * jj + 1] = k1;
+        }
       }
+    }
+    // While this batch is sorted in shared memory the memory system is idle: have the next batch brought into L2 (one bulk
+    // prefetch per array, issued by one thread), so that its loads do not wait for DRAM.
+    if (t == 0 && base + BATCH < n)
+    {
+      const unsigned nn = min(n - (base + BATCH), (unsigned)BATCH);
+      l2_prefetch(rec + base + BATCH, (nn * 8u + 15u) & ~15u);
+      l2_prefetch(key + base + BATCH, (nn * 2u + 15u) & ~15u);
+      if (MASS)
+        l2_prefetch(mass + base + BATCH, (nn * 4u + 15u) & ~15u);
     }
 #pragma unroll
     for (int j = 0; j < PER; j++)
@@ -339,18 +376,15 @@ __global__ void __launch_bounds__(THREADS, CTAS) bin_scatter_kernel(const __grid
       D.rec_s[dst] = sm.rec[i];
     }
     __syncthreads();
-    if (mass)
+    if (MASS)
     { // same permutation for the masses
 #pragma unroll
       for (int j = 0; j < PER; j++)
         if (k[j] != 0xffffffffu)
-          smass[sm.lstart[k[j] & 0xffffu] + (k[j] >> 16)] = mass[base + j * THREADS + t];
+          smass[sm.lstart[k[j] & 0xffffu] + (k[j] >> 16)] = mass[base + rec_index(j)];
       __syncthreads();
       for (unsigned i = t; i < ntot; i += THREADS)
-      {
-        const unsigned b = sm.bin[i];
-        D.mass_s[sm.gcur[b] + (i - sm.lstart[b])] = smass[i];
-      }
+        D.mass_s[sm.gcur[sm.bin[i]] + (i - sm.lstart[sm.bin[i]])] = smass[i];
       __syncthreads();
     }
 #pragma unroll
@@ -364,19 +398,29 @@ using ScatterWin = ScatterSmem<MAX_BINS, SCATTER_THREADS, SCATTER_PER>;
 
 static inline cudaError_t prepare_bin_scatter()
 {
-  cudaError_t e = cudaFuncSetAttribute(bin_scatter_kernel<SMALL_BINS, false, SCATTER_THREADS, SCATTER_PER, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(ScatterSmall));
-  return e != cudaSuccess ? e
-                          : cudaFuncSetAttribute(bin_scatter_kernel<MAX_BINS, true, SCATTER_THREADS, SCATTER_PER, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)sizeof(ScatterWin));
+  cudaError_t e = cudaSuccess;
+  auto prep = [&](auto kern, size_t bytes) {
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  };
+  prep(bin_scatter_kernel<SMALL_BINS, false, false, SCATTER_THREADS, SCATTER_PER, 1>, sizeof(ScatterSmall));
+  prep(bin_scatter_kernel<SMALL_BINS, false, true, SCATTER_THREADS, SCATTER_PER, 1>, sizeof(ScatterSmall));
+  prep(bin_scatter_kernel<MAX_BINS, true, false, SCATTER_THREADS, SCATTER_PER, 1>, sizeof(ScatterWin));
+  prep(bin_scatter_kernel<MAX_BINS, true, true, SCATTER_THREADS, SCATTER_PER, 1>, sizeof(ScatterWin));
+  return e;
 }
 
 static inline void launch_bin_scatter(const SortDev &Q, bool windowed, cudaStream_t stream)
 {
-  if (!windowed && Q.nbins <= SMALL_BINS)
-    bin_scatter_kernel<SMALL_BINS, false, SCATTER_THREADS, SCATTER_PER, 1><<<Q.nregions, SCATTER_THREADS, sizeof(ScatterSmall), stream>>>(Q);
+  const bool small = !windowed && Q.nbins <= SMALL_BINS;
+  if (small && !Q.mass_u)
+    bin_scatter_kernel<SMALL_BINS, false, false, SCATTER_THREADS, SCATTER_PER, 1><<<Q.nregions, SCATTER_THREADS, sizeof(ScatterSmall), stream>>>(Q);
+  else if (small)
+    bin_scatter_kernel<SMALL_BINS, false, true, SCATTER_THREADS, SCATTER_PER, 1><<<Q.nregions, SCATTER_THREADS, sizeof(ScatterSmall), stream>>>(Q);
+  else if (!Q.mass_u)
+    bin_scatter_kernel<MAX_BINS, true, false, SCATTER_THREADS, SCATTER_PER, 1><<<Q.nregions, SCATTER_THREADS, sizeof(ScatterWin), stream>>>(Q);
   else
-    bin_scatter_kernel<MAX_BINS, true, SCATTER_THREADS, SCATTER_PER, 1><<<Q.nregions, SCATTER_THREADS, sizeof(ScatterWin), stream>>>(Q);
+    bin_scatter_kernel<MAX_BINS, true, true, SCATTER_THREADS, SCATTER_PER, 1><<<Q.nregions, SCATTER_THREADS, sizeof(ScatterWin), stream>>>(Q);
 }
 
 // K3: one CTA per (plane, tile) bin
@@ -443,49 +487,69 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
     }
     else
     {
-    float wx[3], wy[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++)
-    {
-      const float cx = __fmul_rn(__fadd_rn((float)(gx + k - 1), 0.5f), L.dlf);
-      const float cy = __fmul_rn(__fadd_rn((float)(gy + k - 1), 0.5f), L.dlf);
-      const float ax = __fmul_rn(fabsf(__fsub_rn(xs, cx)), L.npixf);
-      const float ay = __fmul_rn(fabsf(__fsub_rn(ys, cy)), L.npixf);
-      float vx, vy;
-      if (k == 1)
-      {
-        vx = __fsub_rn(0.75f, __fmul_rn(ax, ax));
-        vy = __fsub_rn(0.75f, __fmul_rn(ay, ay));
-      }
-      else
-      {
-        const float t1 = __fsub_rn(1.5f, ax), t2 = __fsub_rn(1.5f, ay);
-        vx = __fmul_rn(0.5f, __fmul_rn(t1, t1));
-        vy = __fmul_rn(0.5f, __fmul_rn(t2, t2));
-      }
-      wx[k] = __fmul_rn(sm, vx);
-      wy[k] = __fmul_rn(sm, vy);
-    }
     const int lx = gx - 1 - x0, ly = gy - 1 - y0; // local index of stencil cell (0,0)
     unsigned *plo = lo + ly * TW + lx, *phi = hi + ly * TW + lx;
+    // one cell: 64-bit add as two 32-bit shared-memory atomics, the carry taken from the returned old value of the low limb
+    auto add_cell = [&](int off, float contribution_scaled) {
+      const unsigned long long v = (unsigned long long)__float2ll_rn(contribution_scaled);
+      const unsigned vl = (unsigned)v, vh = (unsigned)(v >> 32);
+      const unsigned old = atomicAdd(plo + off, vl);
+      atomicAdd(phi + off, vh + (unsigned)(((unsigned long long)old + vl) >> 32));
+    };
     if (gx >= 1 && gx <= nn - 2 && gy >= 1 && gy <= nn - 2)
     {
-      // interior stencil (all but the map's border): nine unconditional limb pairs, no branches — adding a zero
-      // limb is harmless and cheaper than testing for it
+      // Interior stencil (all but the map's border).  npix is a power of two (PassParams::fast), so scaling by npix or dl is
+      // exact and the reference's |xs - cx_k| / dl (utilities.cpp:4-16,78-89; chain::deposit_pow2) can be evaluated on the
+      // scaled coordinate: with X = xs * npix >= 1 and f = X - floor(X) (exact), X - (gx + k - 1/2) and f - (k - 1/2) are the
+      // same real number, hence the same float after the one rounding of the subtraction.  Likewise the fixed-point scale
+      // 2^frac_bits is folded into the x weights: fl(sm 2^b vx) fl(sm vy) rounds exactly like 2^b fl(fl(sm vx) fl(sm vy)),
+      // and where the unscaled product would be denormal both forms convert to 0.
       SLICER_CHECK(lx >= 0 && lx + 2 < TW && ly >= 0 && ly + 2 < TW); // the record belongs to this tile (+ halo)
+      const float fx = __fsub_rn(__fmul_rn(xs, L.npixf), (float)gx), fy = __fsub_rn(__fmul_rn(ys, L.npixf), (float)gy);
+      const float ax0 = fabsf(__fadd_rn(fx, 0.5f)), ax1 = fabsf(__fsub_rn(fx, 0.5f)), ax2 = fabsf(__fsub_rn(fx, 1.5f));
+      const float ay0 = fabsf(__fadd_rn(fy, 0.5f)), ay1 = fabsf(__fsub_rn(fy, 0.5f)), ay2 = fabsf(__fsub_rn(fy, 1.5f));
+      const float tx0 = __fsub_rn(1.5f, ax0), tx2 = __fsub_rn(1.5f, ax2), ty0 = __fsub_rn(1.5f, ay0), ty2 = __fsub_rn(1.5f, ay2);
+      const float smx = __fmul_rn(sm, L.scalef);
+      float wx[3], wy[3];
+      wx[0] = __fmul_rn(smx, __fmul_rn(0.5f, __fmul_rn(tx0, tx0)));
+      wx[1] = __fmul_rn(smx, __fsub_rn(0.75f, __fmul_rn(ax1, ax1)));
+      wx[2] = __fmul_rn(smx, __fmul_rn(0.5f, __fmul_rn(tx2, tx2)));
+      wy[0] = __fmul_rn(sm, __fmul_rn(0.5f, __fmul_rn(ty0, ty0)));
+      wy[1] = __fmul_rn(sm, __fsub_rn(0.75f, __fmul_rn(ay1, ay1)));
+      wy[2] = __fmul_rn(sm, __fmul_rn(0.5f, __fmul_rn(ty2, ty2)));
+      // nine unconditional limb pairs, no branches — adding a zero limb is harmless and cheaper than testing for it
 #pragma unroll
       for (int jy = 0; jy < 3; jy++)
 #pragma unroll
         for (int jx = 0; jx < 3; jx++)
-        {
-          const unsigned long long v = (unsigned long long)chain::to_fixed(__fmul_rn(wx[jx], wy[jy]), L);
-          const unsigned vl = (unsigned)v, vh = (unsigned)(v >> 32);
-          const unsigned old = atomicAdd(plo + jy * TW + jx, vl);
-          atomicAdd(phi + jy * TW + jx, vh + ((old + vl < old) ? 1u : 0u));
-        }
+          add_cell(jy * TW + jx, __fmul_rn(wx[jx], wy[jy]));
     }
     else
     {
+      // border stencil: the reference's arithmetic operation for operation (xs * npix may be negative here)
+      float wx[3], wy[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+      {
+        const float cx = __fmul_rn(__fadd_rn((float)(gx + k - 1), 0.5f), L.dlf);
+        const float cy = __fmul_rn(__fadd_rn((float)(gy + k - 1), 0.5f), L.dlf);
+        const float ax = __fmul_rn(fabsf(__fsub_rn(xs, cx)), L.npixf);
+        const float ay = __fmul_rn(fabsf(__fsub_rn(ys, cy)), L.npixf);
+        float vx, vy;
+        if (k == 1)
+        {
+          vx = __fsub_rn(0.75f, __fmul_rn(ax, ax));
+          vy = __fsub_rn(0.75f, __fmul_rn(ay, ay));
+        }
+        else
+        {
+          const float t1 = __fsub_rn(1.5f, ax), t2 = __fsub_rn(1.5f, ay);
+          vx = __fmul_rn(0.5f, __fmul_rn(t1, t1));
+          vy = __fmul_rn(0.5f, __fmul_rn(t2, t2));
+        }
+        wx[k] = __fmul_rn(sm, vx);
+        wy[k] = __fmul_rn(sm, vy);
+      }
       for (int jy = 0; jy < 3; jy++)
         for (int jx = 0; jx < 3; jx++)
         {
@@ -493,10 +557,7 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
           if (cx < 0 || cx >= nn || cy < 0 || cy >= nn)
             continue; // utilities.cpp:91 drops cells outside the map
           SLICER_CHECK(lx + jx >= 0 && lx + jx < TW && ly + jy >= 0 && ly + jy < TW);
-          const unsigned long long v = (unsigned long long)chain::to_fixed(__fmul_rn(wx[jx], wy[jy]), L);
-          const unsigned vl = (unsigned)v, vh = (unsigned)(v >> 32);
-          const unsigned old = atomicAdd(plo + jy * TW + jx, vl);
-          atomicAdd(phi + jy * TW + jx, vh + ((old + vl < old) ? 1u : 0u));
+          add_cell(jy * TW + jx, __fmul_rn(__fmul_rn(wx[jx], wy[jy]), L.scalef));
         }
     }
     }
