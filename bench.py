@@ -353,14 +353,25 @@ def run_light_cones(wl: Workload, steps, warmup, world, barrier, max_over_ranks)
     s = wl.s
     ngr = wl.W["ngroups"]
 
+    def finish(slot):
+        # the planes of a pass are finished once the pairs it left to the host's libm are settled (and, at N > 1, summed onto
+        # rank 0 on the communication stream); both wait for that pass only
+        if world > 1:
+            s.reduce_slots(slot, LENS_PER_SNAP, 0)
+        else:
+            s.settle_slots(slot, LENS_PER_SNAP)
+
     def light_cone():
+        # two ranges of accumulator slots: the next pass is submitted before the previous one is finished off, so the device
+        # does not wait for the host in between; every plane is final (in HBM, on rank 0) when the light cone returns
+        prev = None
         for g in range(ngr):
             slot = (g & 1) * LENS_PER_SNAP
             s.deposit_slots(wl.groups[g], slot)
-            if world > 1:
-                s.reduce_slots(slot, LENS_PER_SNAP, 0)  # settles the deferred pairs, then sums onto rank 0 on the comm stream
-            else:
-                s.synchronize()                         # settles the deferred pairs: the finished planes are in HBM
+            if prev is not None:
+                finish(prev)
+            prev = slot
+        finish(prev)
 
     for _ in range(warmup):
         light_cone()

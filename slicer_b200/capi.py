@@ -88,7 +88,7 @@ EXPORTS = [
     "slicer_frac_bits", "slicer_comm_unique_id", "slicer_comm_init_rank", "slicer_comm_init_all",
     "slicer_reduce_all", "slicer_wait_staging", "slicer_count_accepted", "slicer_deposit_degraded", "slicer_reset_stats", "slicer_timer_begin", "slicer_timer_end",
     "slicer_selftest_arith", "slicer_deposit_slots", "slicer_reduce_slots", "slicer_reduce_all_slots",
-    "slicer_stage_synthetic_window",
+    "slicer_stage_synthetic_window", "slicer_settle_slots",
 ]
 
 
@@ -135,6 +135,7 @@ def lib() -> C.CDLL:
     L.slicer_reduce.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.slicer_deposit_slots.argtypes = [C.c_void_p, C.POINTER(PlaneDesc), C.c_int, C.c_int, C.c_int]
     L.slicer_reduce_slots.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.slicer_settle_slots.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.slicer_reduce_all_slots.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int]
     L.slicer_count_accepted.argtypes = [C.c_void_p, C.POINTER(PlaneDesc), C.c_int, C.c_void_p]
     L.slicer_deposit_degraded.argtypes = [C.c_void_p, C.POINTER(PlaneDesc), C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int]
@@ -330,6 +331,11 @@ class Slicer:
 
     def synchronize(self):
         _check(lib().slicer_synchronize(self.h))
+
+    def settle_slots(self, first_slot: int, nplanes: int):
+        """Settle the pairs the passes into these accumulator slots left to the host's libm, without waiting for passes into
+        other slots submitted since."""
+        _check(lib().slicer_settle_slots(self.h, int(first_slot), int(nplanes)))
 
     def wait_staging(self):
         _check(lib().slicer_wait_staging(self.h))

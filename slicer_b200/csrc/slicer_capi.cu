@@ -162,16 +162,33 @@ struct slicer_handle
     PassParams P;
     unsigned long long epoch[SLICER_MAX_PLANES]; // zeroing count of the accumulator slot of device plane k when the pass was submitted
   };
-  struct
+  // Two banks: the passes of one set of planes (a non-accumulating pass and the accumulating ones behind it) append to one
+  // bank, the next set to the other, so that a set can be settled — waiting for ITS last pass only, with the few deposits
+  // on a stream of their own — while the passes of the next set run (slicer_settle_slots, slicer_reduce_slots).
+  struct DeferBank
   {
     DeferEntry *buf = nullptr;
-    unsigned *count = nullptr;
-    DeferEntry *host = nullptr; // pinned mirror
-    unsigned *host_count = nullptr; // pinned: the counter as of the end of the last pass (copied behind every pass)
+    unsigned *count = nullptr;      // device: entries appended since the bank was last settled
+    DeferEntry *host = nullptr;     // pinned mirror
+    unsigned *host_count = nullptr; // pinned: the counter as of the end of the bank's last pass (copied behind every pass)
+    std::vector<SavedPass> passes;  // passes since the last settle; DeferEntry::pass indexes it
+    cudaEvent_t ev_done = nullptr;  // behind the bank's last pass and the copies of its counter / list head
+    unsigned slot_mask = 0;         // accumulator slots the bank's passes deposit into
+  };
+  struct
+  {
+    DeferBank bank[2];
+    int cur = 0;
     unsigned cap = 0;
-    std::vector<SavedPass> passes; // passes since the last resolve; DeferEntry::pass indexes it
     bool failed = false;
   } defer;
+  unsigned *d_ovf = nullptr;        // device flag: an accumulator ran past 2^63 (raised at read-out)
+  cudaStream_t settle = nullptr;    // deposits of the pairs libm settled, beside the passes running on `compute`
+  cudaEvent_t ev_settled = nullptr; // settle -> compute / comm_stream
+  bool settle_pending = false;      // `compute` has not yet waited for ev_settled
+  bool settle_pending_comm = false; // nor has `comm_stream`
+  cudaEvent_t slot_pass_ev[SLICER_MAX_PLANES]; // the stop event (pass_ev ring) of the last pass into accumulator slot q, or nullptr
+  bool fence_all = false;           // something other than a pass wrote accumulators on `compute` (degraded deposit): the next reduce waits for the whole stream
   unsigned long long slot_epoch[SLICER_MAX_PLANES];
   size_t pos_stride = 0, mass_stride = 0; // floats per staging pool (16-byte multiples)
   size_t pcap = 0, mcap = 0;              // particles / masses a pool holds, padding of the segments included
@@ -260,6 +277,7 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
   {
     h->ev_slot[q] = nullptr;
     h->slot_reducing[q] = false;
+    h->slot_pass_ev[q] = nullptr;
   }
   h->cfg = *cfg;
   h->frac_bits = cfg->frac_bits > 0 ? cfg->frac_bits : 40;
@@ -314,6 +332,10 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
     TRY(cudaStreamCreateWithFlags(&h->copy, cudaStreamNonBlocking));
     TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
     TRY(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+    TRY(cudaStreamCreateWithFlags(&h->settle, cudaStreamNonBlocking));
+    TRY(cudaEventCreateWithFlags(&h->ev_settled, cudaEventDisableTiming));
+    TRY(cudaEventCreateWithFlags(&h->defer.bank[0].ev_done, cudaEventDisableTiming));
+    TRY(cudaEventCreateWithFlags(&h->defer.bank[1].ev_done, cudaEventDisableTiming));
     TRY(cudaEventCreateWithFlags(&h->ev_zero_start, cudaEventDisableTiming));
     TRY(cudaEventCreateWithFlags(&h->ev_zero_done, cudaEventDisableTiming));
     TRY(cudaEventCreateWithFlags(&h->ev_pass_done, cudaEventDisableTiming));
@@ -348,20 +370,24 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
       break;
     if (cfg->mass_capacity && (rc = dev_alloc(h, &h->d_mass_pool, h->nbuf * h->mass_stride)))
       break;
-    h->defer.cap = 1u << 20;
-    if ((rc = dev_alloc(h, &h->defer.buf, (size_t)h->defer.cap)) || (rc = dev_alloc(h, &h->defer.count, 2))) // [1]: accumulator overflow flag
+    h->defer.cap = 1u << 19;
+    if ((rc = dev_alloc(h, &h->d_ovf, 1)))
       break;
-    if (cudaHostAlloc((void **)&h->defer.host, (size_t)h->defer.cap * sizeof(DeferEntry), cudaHostAllocDefault) != cudaSuccess)
+    for (int b = 0; b < 2 && !rc; b++)
     {
-      rc = fail("cudaHostAlloc failed: %s", cudaGetErrorString(cudaGetLastError()));
-      break;
+      slicer_handle::DeferBank &B = h->defer.bank[b];
+      if ((rc = dev_alloc(h, &B.buf, (size_t)h->defer.cap)) || (rc = dev_alloc(h, &B.count, 1)))
+        break;
+      if (cudaHostAlloc((void **)&B.host, (size_t)h->defer.cap * sizeof(DeferEntry), cudaHostAllocDefault) != cudaSuccess ||
+          cudaHostAlloc((void **)&B.host_count, 2 * sizeof(unsigned), cudaHostAllocDefault) != cudaSuccess)
+      {
+        rc = fail("cudaHostAlloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        break;
+      }
+      B.host_count[0] = 0;
     }
-    if (cudaHostAlloc((void **)&h->defer.host_count, 2 * sizeof(unsigned), cudaHostAllocDefault) != cudaSuccess)
-    {
-      rc = fail("cudaHostAlloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc)
       break;
-    }
-    h->defer.host_count[0] = 0;
     memset(h->slot_epoch, 0, sizeof(h->slot_epoch));
     h->d_pos = h->d_pos_pool;
     h->d_mass = h->d_mass_pool;
@@ -381,7 +407,9 @@ extern "C" int slicer_create(const slicer_config *cfg, slicer_handle **out)
     }
     if (cudaMemsetAsync(h->d_acc, 0, (size_t)cfg->max_planes * h->ntypes_alloc * h->npix2max * 8, h->compute) != cudaSuccess ||
         cudaMemsetAsync(h->d_counts, 0, (size_t)SLICER_MAX_PLANES * SLICER_NTYPES * 2 * 8, h->compute) != cudaSuccess ||
-        cudaMemsetAsync(h->defer.count, 0, 2 * sizeof(unsigned), h->compute) != cudaSuccess ||
+        cudaMemsetAsync(h->defer.bank[0].count, 0, sizeof(unsigned), h->compute) != cudaSuccess ||
+        cudaMemsetAsync(h->defer.bank[1].count, 0, sizeof(unsigned), h->compute) != cudaSuccess ||
+        cudaMemsetAsync(h->d_ovf, 0, sizeof(unsigned), h->compute) != cudaSuccess ||
         cudaStreamSynchronize(h->compute) != cudaSuccess)
     {
       rc = fail("initial memset failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -427,12 +455,26 @@ extern "C" void slicer_destroy(slicer_handle *h)
   cudaFree(h->bin.bin_count);
   cudaFree(h->bin.bin_start);
   cudaFree(h->bin.region_hist);
-  cudaFree(h->defer.buf);
-  cudaFree(h->defer.count);
-  if (h->defer.host)
-    cudaFreeHost(h->defer.host);
-  if (h->defer.host_count)
-    cudaFreeHost(h->defer.host_count);
+  if (h->settle)
+  {
+    cudaStreamSynchronize(h->settle);
+    cudaStreamDestroy(h->settle);
+  }
+  if (h->ev_settled)
+    cudaEventDestroy(h->ev_settled);
+  cudaFree(h->d_ovf);
+  for (int b = 0; b < 2; b++)
+  {
+    slicer_handle::DeferBank &B = h->defer.bank[b];
+    cudaFree(B.buf);
+    cudaFree(B.count);
+    if (B.host)
+      cudaFreeHost(B.host);
+    if (B.host_count)
+      cudaFreeHost(B.host_count);
+    if (B.ev_done)
+      cudaEventDestroy(B.ev_done);
+  }
   cudaFree(h->d_pos_pool);
   cudaFree(h->d_mass_pool);
   cudaFree(h->d_acc);
@@ -1118,23 +1160,26 @@ static bool host_project(const DeferEntry &e, const PlaneDev &L, float *xs, floa
   return true;
 }
 
-// Settle every particle the lean exact phase deferred since the last call.  Blocks until the passes submitted so far are done.
-static int resolve_deferred(slicer_handle *h)
+// Settle the particles the passes of one bank deferred: waits for the bank's last pass (not for what was submitted to the
+// compute stream after it), evaluates them with libm and deposits the accepted ones on the settle stream.
+static int resolve_bank(slicer_handle *h, int bi)
 {
-  if (h->defer.passes.empty())
+  slicer_handle::DeferBank &B = h->defer.bank[bi];
+  if (B.passes.empty())
     return 0;
   if (set_device(h))
     return 1;
-  // run_pass copies the counter and the head of the list to pinned memory behind every pass: one synchronisation settles the
-  // usual case (a few thousand entries), without further round trips
-  CU(cudaStreamSynchronize(h->compute));
-  const unsigned n = h->defer.host_count[0];
+  // run_pass copies the counter and the head of the list to pinned memory behind every pass: one wait settles the usual
+  // case (a few thousand entries), without further round trips
+  CU(cudaEventSynchronize(B.ev_done));
+  const unsigned n = B.host_count[0];
   if (n > h->defer.cap)
   {
     h->defer.failed = true;
-    h->defer.passes.clear();
-    CU(cudaMemsetAsync(h->defer.count, 0, sizeof(unsigned), h->compute));
-    h->defer.host_count[0] = 0;
+    B.passes.clear();
+    B.slot_mask = 0;
+    CU(cudaMemsetAsync(B.count, 0, sizeof(unsigned), h->compute));
+    B.host_count[0] = 0;
     return fail("%u particles within the rounding guard of a decision boundary exceed the deferred buffer (%u): the planes deposited since the "
                 "last fetch are incomplete; deposit and fetch in smaller batches",
                 n, h->defer.cap);
@@ -1143,18 +1188,17 @@ static int resolve_deferred(slicer_handle *h)
   {
     if (n > DEFER_HEAD)
     {
-      CU(cudaMemcpyAsync(h->defer.host + DEFER_HEAD, h->defer.buf + DEFER_HEAD, (size_t)(n - DEFER_HEAD) * sizeof(DeferEntry), cudaMemcpyDeviceToHost,
-                         h->compute));
-      CU(cudaStreamSynchronize(h->compute));
+      CU(cudaMemcpyAsync(B.host + DEFER_HEAD, B.buf + DEFER_HEAD, (size_t)(n - DEFER_HEAD) * sizeof(DeferEntry), cudaMemcpyDeviceToHost, h->settle));
+      CU(cudaStreamSynchronize(h->settle));
     }
-    const size_t np = h->defer.passes.size();
+    const size_t np = B.passes.size();
     std::vector<std::vector<ResolvedRec>> out(np);
     for (unsigned i = 0; i < n; i++)
     {
-      const DeferEntry &e = h->defer.host[i];
+      const DeferEntry &e = B.host[i];
       if (e.pass >= np || e.plane >= SLICER_MAX_PLANES)
         return fail("corrupt deferred entry (internal error)");
-      const slicer_handle::SavedPass &sp = h->defer.passes[e.pass];
+      const slicer_handle::SavedPass &sp = B.passes[e.pass];
       const PlaneDev &L = sp.P.pl[e.plane];
       if (sp.epoch[e.plane] != h->slot_epoch[L.slot])
       {
@@ -1170,8 +1214,9 @@ static int resolve_deferred(slicer_handle *h)
       r.type = e.type;
       out[e.pass].push_back(r);
     }
-    ResolvedRec *dev = reinterpret_cast<ResolvedRec *>(h->defer.buf);
-    ResolvedRec *stage = reinterpret_cast<ResolvedRec *>(h->defer.host);
+    // (the list itself is the staging area of the settled pairs: the bank's passes are over, nothing appends to it)
+    ResolvedRec *dev = reinterpret_cast<ResolvedRec *>(B.buf);
+    ResolvedRec *stage = reinterpret_cast<ResolvedRec *>(B.host);
     size_t off = 0;
     for (size_t k = 0; k < np; k++)
     {
@@ -1179,20 +1224,59 @@ static int resolve_deferred(slicer_handle *h)
       if (!m)
         continue;
       memcpy(stage + off, out[k].data(), (size_t)m * sizeof(ResolvedRec));
-      CU(cudaMemcpyAsync(dev + off, stage + off, (size_t)m * sizeof(ResolvedRec), cudaMemcpyHostToDevice, h->compute));
+      CU(cudaMemcpyAsync(dev + off, stage + off, (size_t)m * sizeof(ResolvedRec), cudaMemcpyHostToDevice, h->settle));
       if (h->cfg.mas == SLICER_MAS_NGP)
-        resolved_deposit_kernel<SLICER_MAS_NGP><<<(m + 127) / 128, 128, 0, h->compute>>>(h->defer.passes[k].P, dev + off, m);
+        resolved_deposit_kernel<SLICER_MAS_NGP><<<(m + 127) / 128, 128, 0, h->settle>>>(B.passes[k].P, dev + off, m);
       else
-        resolved_deposit_kernel<SLICER_MAS_TSC><<<(m + 127) / 128, 128, 0, h->compute>>>(h->defer.passes[k].P, dev + off, m);
+        resolved_deposit_kernel<SLICER_MAS_TSC><<<(m + 127) / 128, 128, 0, h->settle>>>(B.passes[k].P, dev + off, m);
       CU(cudaGetLastError());
       h->stats.launches++;
       off += m;
     }
-    CU(cudaMemsetAsync(h->defer.count, 0, sizeof(unsigned), h->compute));
-    h->defer.host_count[0] = 0;
-    // (no synchronisation here: the next call synchronises the stream before it touches the pinned mirror again)
+    CU(cudaMemsetAsync(B.count, 0, sizeof(unsigned), h->settle));
+    B.host_count[0] = 0;
+    // whatever touches the accumulators or this bank next (a pass, a read-out, a reduce) waits for these on the device;
+    // the next use of the pinned mirror is behind the next cudaEventSynchronize(B.ev_done), which these precede in stream order
+    CU(cudaEventRecord(h->ev_settled, h->settle));
+    h->settle_pending = h->settle_pending_comm = true;
   }
-  h->defer.passes.clear();
+  B.passes.clear();
+  B.slot_mask = 0;
+  return 0;
+}
+
+// Settle what the passes into accumulator slots [lo, lo + n) deferred (n < 0: every pass submitted so far): the older bank first.
+static int resolve_deferred(slicer_handle *h, int lo = 0, int n = -1)
+{
+  unsigned mask = 0xffffffffu;
+  if (n >= 0)
+  {
+    mask = 0;
+    for (int q = lo; q < lo + n && q < SLICER_MAX_PLANES; q++)
+      mask |= 1u << q;
+  }
+  for (int k = 1; k <= 2; k++)
+  {
+    const int bi = (h->defer.cur + k) & 1;
+    if ((h->defer.bank[bi].slot_mask & mask) && resolve_bank(h, bi))
+      return 1;
+  }
+  return 0;
+}
+
+// the compute stream (or the communication stream) must see the deposits of the settled pairs before it touches accumulators
+static int wait_settled(slicer_handle *h, bool comm)
+{
+  if (!comm && h->settle_pending)
+  {
+    CU(cudaStreamWaitEvent(h->compute, h->ev_settled, 0));
+    h->settle_pending = false;
+  }
+  if (comm && h->settle_pending_comm)
+  {
+    CU(cudaStreamWaitEvent(h->comm_stream, h->ev_settled, 0));
+    h->settle_pending_comm = false;
+  }
   return 0;
 }
 
@@ -1230,7 +1314,16 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
     CU(cudaStreamWaitEvent(h->compute, h->ev_copy, 0));
     h->copy_pending = false;
   }
-  if (h->defer.passes.size() >= 4096 && resolve_deferred(h))
+  // a new set of planes takes the other bank (settled first, if the caller has not done so: its passes are two sets back)
+  if (!accumulate)
+  {
+    h->defer.cur ^= 1;
+    if (resolve_bank(h, h->defer.cur))
+      return 1;
+  }
+  if (h->defer.bank[h->defer.cur].passes.size() >= 4096 && resolve_bank(h, h->defer.cur))
+    return 1;
+  if (wait_settled(h, false))
     return 1;
   if (!accumulate)
   {
@@ -1253,17 +1346,21 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
     for (int q = first_slot; q < first_slot + nplanes; q++)
       h->slot_epoch[q]++; // deferred particles of earlier passes into these accumulators are void
   }
+  slicer_handle::DeferBank &B = h->defer.bank[h->defer.cur];
   DeferDev F;
-  F.buf = h->defer.buf;
-  F.count = h->defer.count;
+  F.buf = B.buf;
+  F.count = B.count;
   F.cap = h->defer.cap;
-  F.pass = (unsigned)h->defer.passes.size();
+  F.pass = (unsigned)B.passes.size();
   { // (any path can defer pairs: the lean projection and the general chain's guard)
     slicer_handle::SavedPass sp;
     sp.P = P;
     for (int k = 0; k < P.nplanes; k++)
+    {
       sp.epoch[k] = h->slot_epoch[P.pl[k].slot];
-    h->defer.passes.push_back(sp);
+      B.slot_mask |= 1u << P.pl[k].slot;
+    }
+    B.passes.push_back(sp);
   }
   int kernel = h->cfg.kernel;
   if (kernel == SLICER_KERNEL_AUTO)
@@ -1309,9 +1406,12 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
   if (maps_ready(h)) // (a pass without particles still leaves zeroed planes behind it in stream order)
     return 1;
   CU(cudaEventRecord(e1, h->compute));
-  // the deferred list as of now, for resolve_deferred
-  CU(cudaMemcpyAsync(h->defer.host_count, h->defer.count, sizeof(unsigned), cudaMemcpyDeviceToHost, h->compute));
-  CU(cudaMemcpyAsync(h->defer.host, h->defer.buf, (size_t)DEFER_HEAD * sizeof(DeferEntry), cudaMemcpyDeviceToHost, h->compute));
+  for (int k = 0; k < P.nplanes; k++)
+    h->slot_pass_ev[P.pl[k].slot] = e1; // (a recycled ring entry stands for a later pass: waiting for it is still sufficient)
+  // the bank's deferred list as of now, for resolve_bank
+  CU(cudaMemcpyAsync(B.host_count, B.count, sizeof(unsigned), cudaMemcpyDeviceToHost, h->compute));
+  CU(cudaMemcpyAsync(B.host, B.buf, (size_t)DEFER_HEAD * sizeof(DeferEntry), cudaMemcpyDeviceToHost, h->compute));
+  CU(cudaEventRecord(B.ev_done, h->compute));
   CU(cudaEventRecord(h->ev_buf_done[h->cur_buf], h->compute));
   h->pass_head++;
   return 0;
@@ -1480,6 +1580,9 @@ extern "C" int slicer_deposit_degraded(slicer_handle *h, const slicer_plane_desc
     return fail("slicer_deposit_degraded: snopt %d outside 1..30", snopt);
   if (!h->deg.valid || h->deg.nplanes < nplanes)
     return fail("slicer_deposit_degraded: call slicer_count_accepted for this batch and these planes first");
+  if (wait_settled(h, false))
+    return 1;
+  h->fence_all = true;
   if (!accumulate)
   {
     CU(cudaMemsetAsync(h->d_acc, 0, (size_t)nplanes * h->ntypes_alloc * h->npix2max * sizeof(unsigned long long), h->compute));
@@ -1551,8 +1654,20 @@ extern "C" int slicer_synchronize(slicer_handle *h)
   if (resolve_deferred(h))
     return 1;
   CU(cudaStreamSynchronize(h->compute));
+  CU(cudaStreamSynchronize(h->settle));
   CU(cudaStreamSynchronize(h->comm_stream));
   return 0;
+}
+
+extern "C" int slicer_settle_slots(slicer_handle *h, int first_slot, int nplanes)
+{
+  if (!h)
+    return fail("null handle");
+  if (nplanes < 1 || first_slot < 0 || first_slot + nplanes > h->cfg.max_planes)
+    return fail("slicer_settle_slots: slots %d..%d outside 0..%d", first_slot, first_slot + nplanes - 1, h->cfg.max_planes - 1);
+  if (set_device(h))
+    return 1;
+  return resolve_deferred(h, first_slot, nplanes);
 }
 
 extern "C" int slicer_wait_staging(slicer_handle *h)
@@ -1586,7 +1701,7 @@ static int check_plane(slicer_handle *h, int plane, int type)
 extern "C" int slicer_fetch(slicer_handle *h, int plane, int type, float *out_map, long long counts[SLICER_NTYPES],
                             long long ingrid[SLICER_NTYPES])
 {
-  if (check_plane(h, plane, type) || resolve_deferred(h) || wait_slot_reduces(h, plane, 1))
+  if (check_plane(h, plane, type) || resolve_deferred(h, plane, 1) || wait_settled(h, false) || wait_slot_reduces(h, plane, 1))
     return 1;
   const size_t npix2 = (size_t)h->plane_npix[plane] * h->plane_npix[plane];
   const unsigned long long *base = h->d_acc + (size_t)plane * h->ntypes_alloc * h->npix2max;
@@ -1595,13 +1710,13 @@ extern "C" int slicer_fetch(slicer_handle *h, int plane, int type, float *out_ma
     const unsigned long long *src = type >= 0 ? base + (size_t)type * h->npix2max : base;
     const int nt = type >= 0 ? 1 : h->ntypes_alloc;
     const int blocks = (int)((npix2 + 255) / 256 < (size_t)h->sm_count * 8 ? (npix2 + 255) / 256 : (size_t)h->sm_count * 8);
-    finalize_map_kernel<<<blocks, 256, 0, h->compute>>>(src, h->npix2max, nt, npix2, ldexp(1.0, -h->frac_bits), h->d_out, h->defer.count + 1);
+    finalize_map_kernel<<<blocks, 256, 0, h->compute>>>(src, h->npix2max, nt, npix2, ldexp(1.0, -h->frac_bits), h->d_out, h->d_ovf);
     CU(cudaGetLastError());
     h->stats.launches++;
     CU(cudaMemcpyAsync(out_map, h->d_out, npix2 * sizeof(float), cudaMemcpyDeviceToHost, h->compute));
   }
   unsigned ovf = 0;
-  CU(cudaMemcpyAsync(&ovf, h->defer.count + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, h->compute));
+  CU(cudaMemcpyAsync(&ovf, h->d_ovf, sizeof(unsigned), cudaMemcpyDeviceToHost, h->compute));
   unsigned long long c[SLICER_NTYPES * 2];
   CU(cudaMemcpyAsync(c, h->d_counts + (size_t)plane * SLICER_NTYPES * 2, sizeof(c), cudaMemcpyDeviceToHost, h->compute));
   CU(cudaStreamSynchronize(h->compute));
@@ -1614,7 +1729,7 @@ extern "C" int slicer_fetch(slicer_handle *h, int plane, int type, float *out_ma
   }
   if (ovf)
   {
-    CU(cudaMemsetAsync(h->defer.count + 1, 0, sizeof(unsigned), h->compute));
+    CU(cudaMemsetAsync(h->d_ovf, 0, sizeof(unsigned), h->compute));
     return fail("plane %d: a fixed-point accumulator exceeded 2^63 (more than %.3g mass units in one pixel at %d fraction bits); "
                 "create the handle with a smaller slicer_config.frac_bits", plane, ldexp(1.0, 63 - h->frac_bits), h->frac_bits);
   }
@@ -1623,7 +1738,7 @@ extern "C" int slicer_fetch(slicer_handle *h, int plane, int type, float *out_ma
 
 extern "C" int slicer_fetch_fixed(slicer_handle *h, int plane, int type, long long *out)
 {
-  if (check_plane(h, plane, type) || resolve_deferred(h) || wait_slot_reduces(h, plane, 1))
+  if (check_plane(h, plane, type) || resolve_deferred(h, plane, 1) || wait_settled(h, false) || wait_slot_reduces(h, plane, 1))
     return 1;
   if (!out)
     return fail("slicer_fetch_fixed: null output");
@@ -1632,16 +1747,16 @@ extern "C" int slicer_fetch_fixed(slicer_handle *h, int plane, int type, long lo
   const unsigned long long *src = type >= 0 ? base + (size_t)type * h->npix2max : base;
   const int nt = type >= 0 ? 1 : h->ntypes_alloc;
   const int blocks = (int)((npix2 + 255) / 256 < (size_t)h->sm_count * 8 ? (npix2 + 255) / 256 : (size_t)h->sm_count * 8);
-  sum_types_kernel<<<blocks, 256, 0, h->compute>>>(src, h->npix2max, nt, npix2, h->d_sum, h->defer.count + 1);
+  sum_types_kernel<<<blocks, 256, 0, h->compute>>>(src, h->npix2max, nt, npix2, h->d_sum, h->d_ovf);
   CU(cudaGetLastError());
   h->stats.launches++;
   CU(cudaMemcpyAsync(out, h->d_sum, npix2 * sizeof(long long), cudaMemcpyDeviceToHost, h->compute));
   unsigned ovf = 0;
-  CU(cudaMemcpyAsync(&ovf, h->defer.count + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, h->compute));
+  CU(cudaMemcpyAsync(&ovf, h->d_ovf, sizeof(unsigned), cudaMemcpyDeviceToHost, h->compute));
   CU(cudaStreamSynchronize(h->compute));
   if (ovf)
   {
-    CU(cudaMemsetAsync(h->defer.count + 1, 0, sizeof(unsigned), h->compute));
+    CU(cudaMemsetAsync(h->d_ovf, 0, sizeof(unsigned), h->compute));
     return fail("plane %d: a fixed-point accumulator exceeded 2^63 (more than %.3g mass units in one pixel at %d fraction bits); "
                 "create the handle with a smaller slicer_config.frac_bits", plane, ldexp(1.0, 63 - h->frac_bits), h->frac_bits);
   }
@@ -1782,9 +1897,28 @@ static int reduce_fence_before(slicer_handle *h, int first_slot, int nplanes)
 {
   if (wait_slot_reduces(h, first_slot, nplanes)) // an earlier reduce of the same slots (same stream anyway)
     return 1;
-  CU(cudaEventRecord(h->ev_pass_done, h->compute));
-  CU(cudaStreamWaitEvent(h->comm_stream, h->ev_pass_done, 0));
-  return 0;
+  // after the last pass into each of these slots (not after passes into other slots submitted since) and after the deposits
+  // of the pairs libm settled
+  bool all = h->fence_all;
+  for (int q = first_slot; q < first_slot + nplanes; q++)
+    all = all || !h->slot_pass_ev[q];
+  if (all)
+  {
+    CU(cudaEventRecord(h->ev_pass_done, h->compute));
+    CU(cudaStreamWaitEvent(h->comm_stream, h->ev_pass_done, 0));
+    h->fence_all = false;
+  }
+  else
+  {
+    cudaEvent_t seen = nullptr;
+    for (int q = first_slot; q < first_slot + nplanes; q++)
+      if (h->slot_pass_ev[q] != seen)
+      {
+        seen = h->slot_pass_ev[q];
+        CU(cudaStreamWaitEvent(h->comm_stream, seen, 0));
+      }
+  }
+  return wait_settled(h, true);
 }
 static int reduce_fence_after(slicer_handle *h, int first_slot, int nplanes)
 {
@@ -1802,7 +1936,7 @@ extern "C" int slicer_reduce_slots(slicer_handle *h, int first_slot, int nplanes
     return fail("null handle");
   if (nplanes < 1 || first_slot < 0 || first_slot + nplanes > h->cfg.max_planes)
     return fail("slicer_reduce: slots %d..%d outside 0..%d", first_slot, first_slot + nplanes - 1, h->cfg.max_planes - 1);
-  if (set_device(h) || resolve_deferred(h))
+  if (set_device(h) || resolve_deferred(h, first_slot, nplanes))
     return 1;
   if (!h->comm || h->nranks == 1)
     return 0;
@@ -1830,7 +1964,7 @@ extern "C" int slicer_reduce_all_slots(slicer_handle **handles, int n, int first
       return fail("slicer_reduce_all: null handle");
     if (nplanes < 1 || first_slot < 0 || first_slot + nplanes > handles[i]->cfg.max_planes)
       return fail("slicer_reduce_all: slots %d..%d outside 0..%d", first_slot, first_slot + nplanes - 1, handles[i]->cfg.max_planes - 1);
-    if (set_device(handles[i]) || resolve_deferred(handles[i]))
+    if (set_device(handles[i]) || resolve_deferred(handles[i], first_slot, nplanes))
       return 1;
   }
   if (n == 1)

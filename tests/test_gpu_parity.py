@@ -625,6 +625,46 @@ def test_deferred_pairs_of_a_zeroed_plane_are_dropped(oracle):
     assert st.flagged_void > 100 and st.flagged_pairs > 100
 
 
+@pytest.mark.parametrize("mode", [capi.DEPOSIT_DIRECT, capi.DEPOSIT_BINNED])
+def test_settle_slots_behind_the_next_pass(oracle, mode):
+    """Two ranges of accumulator slots, as bench.py and a pipelined caller use them: the next pass is submitted BEFORE the
+    pairs the previous one left to the host's libm are settled (slicer_settle_slots waits for that pass only and deposits on a
+    stream of its own).  With the guard widened to 2^-34 thousands of pairs per pass go that way; every plane must equal the
+    oracle's bit for bit, whichever pass ran beside its settling, and a third pass into the first slots must not see them."""
+    box = 128000.0
+    n = 1 << 20
+    pos = synth.uniform_positions(n, box, 31)
+    types = [dict(type=1, raw=pos, const_mass=1.0375)]
+    npix = 256
+    planes = [dict(boxsize=box, sgn=[-1, 1, -1], face=5, centre=[0.75, 0.125, 0.5], rcase=1.0, ld=128.0 + 16, ld2=256.0, nrepperp=0, fovradiants=0.55),
+              dict(boxsize=box, sgn=[1, -1, 1], face=2, centre=[0.25, 0.625, 0.375], rcase=0.0, ld=40.0, ld2=128.0, nrepperp=0, fovradiants=0.55),
+              dict(boxsize=box, sgn=[1, 1, -1], face=4, centre=[0.5, 0.875, 0.125], rcase=1.0, ld=128.0, ld2=200.0, nrepperp=0, fovradiants=0.55)]
+    with capi.Slicer(npix_max=npix, max_planes=2, mas=capi.MAS_TSC, particle_capacity=n + 64, deposit_mode=mode, guard_eta=2.0 ** -34) as s:
+        s.begin_snapshot(box, [0, 1.0375, 0, 0, 0, 0], False)
+        s.stage(1, pos)
+        fb = s.frac_bits
+        want = [oracle.plane_from_particles(types, p, npix, frac_bits=fb) for p in planes]
+        descs = [capi.plane_desc(p["sgn"], p["face"], p["centre"], p["rcase"], p["ld"], p["ld2"], p["fovradiants"], npix) for p in planes]
+        settled = []
+        prev = None
+        for g, d in enumerate(descs):
+            slot = g & 1
+            s.deposit_slots([d], slot)
+            if prev is not None:
+                f0 = int(s.stats().flagged_pairs)
+                s.settle_slots(prev[1], 1)
+                settled.append(int(s.stats().flagged_pairs) - f0)
+                _, counts, ingrid = s.fetch(prev[1], -1, npix, want_map=False)
+                assert counts.tolist() == want[prev[0]]["counts"].tolist() and ingrid.tolist() == want[prev[0]]["ingrid"].tolist()
+                assert np.array_equal(s.fetch_fixed(prev[1], -1, npix).reshape(-1), want[prev[0]]["fixed"][1])
+            prev = (g, slot)
+        s.settle_slots(prev[1], 1)
+        assert np.array_equal(s.fetch_fixed(prev[1], -1, npix).reshape(-1), want[prev[0]]["fixed"][1])
+        # the other range still holds the second plane, untouched by the third pass and its settling
+        assert np.array_equal(s.fetch_fixed(1, -1, npix).reshape(-1), want[1]["fixed"][1])
+    assert all(v > 1000 for v in settled), settled
+
+
 def test_binned_dense_pass_with_two_randomisations(oracle):
     """Two randomisations whose planes together accept most of the snapshot, in ONE binned pass: a particle then yields up to two
     records, so a K1 CTA emits more records than it streams particles (the record regions must be sized for that)."""
