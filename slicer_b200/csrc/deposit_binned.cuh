@@ -423,70 +423,11 @@ static inline void launch_bin_scatter(const SortDev &Q, bool windowed, cudaStrea
     bin_scatter_kernel<MAX_BINS, true, true, SCATTER_THREADS, SCATTER_PER, 1><<<Q.nregions, SCATTER_THREADS, sizeof(ScatterWin), stream>>>(Q);
 }
 
-// K3: one CTA per (plane, tile) bin
-template <int MAS>
-__global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
-    tile_deposit_kernel(const __grid_constant__ PassParams P, const __grid_constant__ SortDev D, int ntile, int ntx, int gshift, int type,
-                        float const_mass)
+// The TSC 3x3 stencil of one record (utilities.cpp:78-94) into the tile: 64-bit cells kept as two 32-bit limbs.
+// (x0, y0) = map cell of local cell (0,0); `sm` = sqrtf(mass).
+__device__ __forceinline__ void tile_tsc(unsigned *lo, unsigned *hi, int x0, int y0, int nn, const PlaneDev &L, float xs, float ys, int gx, int gy,
+                                         float sm)
 {
-  extern __shared__ __align__(16) unsigned tile_smem[];
-  __shared__ unsigned s_ingrid, s_n;
-  unsigned *lo = tile_smem;
-  unsigned *hi = tile_smem + TCELLS;
-  const int bl = blockIdx.x >> gshift, sub = blockIdx.x & ((1 << gshift) - 1); // bin of this launch, tile within the bin's group
-  const unsigned r0 = D.bin_start[bl], r1 = D.bin_start[bl + 1];
-  if (r0 == r1)
-    return;
-  if (threadIdx.x == 0)
-  {
-    s_ingrid = 0;
-    s_n = 0;
-  }
-  const int b = bl + D.bin_lo;
-  const int q = b / (ntile * ntx);
-  const int tb = b - q * ntile * ntx;
-  const int ty = tb / ntx, tx = ((tb - ty * ntx) << gshift) + sub;
-  if (tx >= ntile)
-    return; // the last group of a row may be incomplete
-  const PlaneDev &L = P.pl[q];
-  const int nn = L.npix;
-  const int x0 = tx * TILE - 1, y0 = ty * TILE - 1; // map cell of local (0,0)
-  // The records of this bin are the accepted pairs of (plane, tile): this kernel keeps mapParticles' counters for the binned
-  // path (densitymaps.cpp:402-403), the record kernel does not count.  Only a border tile can hold records whose nearest
-  // grid point is outside the map.
-  const bool border = tx == 0 || ty == 0 || tx == ntile - 1 || ty == ntile - 1;
-  unsigned my_ingrid = 0, my_n = 0; // (my_n: records of THIS tile when the bin holds a group of tiles)
-  for (int i = threadIdx.x; i < 2 * TCELLS; i += DEPOSIT_THREADS)
-    tile_smem[i] = 0;
-  __syncthreads();
-  // `sm` = sqrtf(mass) (utilities.cpp:86-89 multiplies each 1-D weight by it); for a constant-mass segment it is hoisted out
-  // of the record loop (the IEEE square root is a guarded sequence of ~15 instructions)
-  const float sm_const = __fsqrt_rn(const_mass);
-  auto one = [&](float xs, float ys, float m, float sm) {
-    const int gx = __float2int_rd(__fmul_rn(xs, L.npixf));
-    const int gy = __float2int_rd(__fmul_rn(ys, L.npixf));
-    if (gshift)
-    { // the bin holds the records of 2^gshift tiles: this CTA deposits its own
-      if (min(max(gx, 0), nn - 1) / TILE != tx)
-        return;
-      my_n++;
-    }
-    if (border)
-      my_ingrid += (gx >= 0 && gx < nn && gy >= 0 && gy < nn) ? 1u : 0u;
-    if constexpr (MAS == SLICER_MAS_NGP)
-    { // utilities.cpp:72-76: the whole mass goes to the nearest grid point, if it is inside the map
-      if (gx >= 0 && gx < nn && gy >= 0 && gy < nn)
-      {
-        const unsigned long long v = (unsigned long long)chain::to_fixed(m, L);
-        const int c = (gy - y0) * TW + gx - x0;
-        SLICER_CHECK(gx - x0 >= 1 && gx - x0 <= TILE && gy - y0 >= 1 && gy - y0 <= TILE);
-        const unsigned vl = (unsigned)v, vh = (unsigned)(v >> 32);
-        const unsigned old = atomicAdd(lo + c, vl);
-        atomicAdd(hi + c, vh + ((old + vl < old) ? 1u : 0u));
-      }
-    }
-    else
-    {
     const int lx = gx - 1 - x0, ly = gy - 1 - y0; // local index of stencil cell (0,0)
     unsigned *plo = lo + ly * TW + lx, *phi = hi + ly * TW + lx;
     // one cell: 64-bit add as two 32-bit shared-memory atomics, the carry taken from the returned old value of the low limb
@@ -560,7 +501,72 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
           add_cell(jy * TW + jx, __fmul_rn(__fmul_rn(wx[jx], wy[jy]), L.scalef));
         }
     }
+}
+
+// K3: one CTA per (plane, tile) bin
+template <int MAS>
+__global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
+    tile_deposit_kernel(const __grid_constant__ PassParams P, const __grid_constant__ SortDev D, int ntile, int ntx, int gshift, int type,
+                        float const_mass)
+{
+  extern __shared__ __align__(16) unsigned tile_smem[];
+  __shared__ unsigned s_ingrid, s_n;
+  unsigned *lo = tile_smem;
+  unsigned *hi = tile_smem + TCELLS;
+  const int bl = blockIdx.x >> gshift, sub = blockIdx.x & ((1 << gshift) - 1); // bin of this launch, tile within the bin's group
+  const unsigned r0 = D.bin_start[bl], r1 = D.bin_start[bl + 1];
+  if (r0 == r1)
+    return;
+  if (threadIdx.x == 0)
+  {
+    s_ingrid = 0;
+    s_n = 0;
+  }
+  const int b = bl + D.bin_lo;
+  const int q = b / (ntile * ntx);
+  const int tb = b - q * ntile * ntx;
+  const int ty = tb / ntx, tx = ((tb - ty * ntx) << gshift) + sub;
+  if (tx >= ntile)
+    return; // the last group of a row may be incomplete
+  const PlaneDev &L = P.pl[q];
+  const int nn = L.npix;
+  const int x0 = tx * TILE - 1, y0 = ty * TILE - 1; // map cell of local (0,0)
+  // The records of this bin are the accepted pairs of (plane, tile): this kernel keeps mapParticles' counters for the binned
+  // path (densitymaps.cpp:402-403), the record kernel does not count.  Only a border tile can hold records whose nearest
+  // grid point is outside the map.
+  const bool border = tx == 0 || ty == 0 || tx == ntile - 1 || ty == ntile - 1;
+  unsigned my_ingrid = 0, my_n = 0; // (my_n: records of THIS tile when the bin holds a group of tiles)
+  for (int i = threadIdx.x; i < 2 * TCELLS; i += DEPOSIT_THREADS)
+    tile_smem[i] = 0;
+  __syncthreads();
+  // `sm` = sqrtf(mass) (utilities.cpp:86-89 multiplies each 1-D weight by it); for a constant-mass segment it is hoisted out
+  // of the record loop (the IEEE square root is a guarded sequence of ~15 instructions)
+  const float sm_const = __fsqrt_rn(const_mass);
+  auto one = [&](float xs, float ys, float m, float sm) {
+    const int gx = __float2int_rd(__fmul_rn(xs, L.npixf));
+    const int gy = __float2int_rd(__fmul_rn(ys, L.npixf));
+    if (gshift)
+    { // the bin holds the records of 2^gshift tiles: this CTA deposits its own
+      if (min(max(gx, 0), nn - 1) / TILE != tx)
+        return;
+      my_n++;
     }
+    if (border)
+      my_ingrid += (gx >= 0 && gx < nn && gy >= 0 && gy < nn) ? 1u : 0u;
+    if constexpr (MAS == SLICER_MAS_NGP)
+    { // utilities.cpp:72-76: the whole mass goes to the nearest grid point, if it is inside the map
+      if (gx >= 0 && gx < nn && gy >= 0 && gy < nn)
+      {
+        const unsigned long long v = (unsigned long long)chain::to_fixed(m, L);
+        const int c = (gy - y0) * TW + gx - x0;
+        SLICER_CHECK(gx - x0 >= 1 && gx - x0 <= TILE && gy - y0 >= 1 && gy - y0 <= TILE);
+        const unsigned vl = (unsigned)v, vh = (unsigned)(v >> 32);
+        const unsigned old = atomicAdd(lo + c, vl);
+        atomicAdd(hi + c, vh + ((old + vl < old) ? 1u : 0u));
+      }
+    }
+    else
+      tile_tsc(lo, hi, x0, y0, nn, L, xs, ys, gx, gy, sm);
   };
   {
     unsigned i = r0 + threadIdx.x;
@@ -616,5 +622,6 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, SLICER_TILE_CTAS)
     }
   }
 }
+
 
 } // namespace binned
