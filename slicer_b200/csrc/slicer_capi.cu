@@ -1013,13 +1013,10 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
     return 1;
   const int nt = binned_tiles(P), gshift = binned_gshift(P), ntx = (nt + (1 << gshift) - 1) >> gshift;
   const int nbins = P.nplanes * nt * ntx;
-  // few accepted particles: one slice as large as the buffers allow (the per-slice fixed costs dominate);
-  // many: 2^28-particle slices (measured optimum at 25-55 % acceptance)
+  // one slice as large as the record buffers allow: the per-slice fixed costs (tile zero + flush, sort set-up, kernel tails) fall
+  // with the number of slices (round 2, with the prefetching scatter: 15.2 -> 14.75 ms on the densest C3 group between 2^28- and
+  // 2^30-particle slices; round 1's scatter had its optimum at 2^28)
   size_t slice = h->bin.slice;
-  // (not for maps of several bin windows: their tiles are sparsely filled, the per-tile zero + flush dominates)
-  // (not for maps of thousands of tiles: their tiles are sparsely filled, the per-tile zero + flush and the per-sort set-up dominate)
-  if (P.est_accept >= 0.12 && (long long)P.nplanes * nt * nt <= 1024 && slice > ((size_t)1 << 28))
-    slice = (size_t)1 << 28;
   // a particle yields up to one record per randomisation of the pass: the slice shrinks so that the regions still fit
   if (P.nxform > 1)
   {

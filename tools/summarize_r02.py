@@ -63,7 +63,7 @@ if os.path.exists(rep):
     out = [f"# Round 02 — `ncu --set full` of the pass kernels ({wlname}, CUDA sources {meta['csrc_sha']})", "",
            "Command (after the same command exited 0 without ncu): `PGROUPS=<dense group> ncu --set full --clock-control none --import-source on "
            "--profile-from-start off -k regex:\"deposit_pipelined|bin_histogram|bin_scatter|tile_deposit\" -c 4 python tools/profile_lightcone.py`", "",
-           "Captured launches: the first slice of the densest group of the light cone.  Times under ncu are cold-cache and serialised.", "",
+           "Captured launches: the kernels of the densest group's pass (one slice).  Times under ncu are cold-cache and serialised.", "",
            "| metric | " + " | ".join(f"launch {i}" for i in range(len(rows) - 2)) + " |", "|---|" + "---|" * (len(rows) - 2)]
 
     def fmt(v):
