@@ -15,8 +15,10 @@
 //                                            32-bit limbs (carry from the returned old value), then flushed once
 //                                            with red.global.add.u64.
 // The int64 sums are exact and order independent, so the result is bit-identical to the direct path.
-// K2/K3 sort and deposit at most MAX_BINS bins at a time: maps with more (plane, tile) bins (8192^2) are handled in windows
-// of the bin range over the SAME records (SortDev::bin_lo), i.e. K1 still runs once.
+// K2/K3 sort and deposit at most MAX_BINS bins at a time: maps with more (plane, tile) pairs (8192^2) sort by groups of 2 or 4
+// tiles adjacent in x (EmitDev::gshift; the tile kernel runs one CTA per tile and skips its neighbours' records), and beyond
+// that in windows of the bin range over the SAME records (SortDev::bin_lo), i.e. K1 still runs once.
+// With at most HIST_BINS bins K2a is folded into K1 (EmitDev::region_hist).
 // Requirements (PassParams::fast): power-of-two npix equal for all planes, no perpendicular replication, <= 65536 bins.
 #pragma once
 #include <cuda_runtime.h>
@@ -51,7 +53,12 @@ struct EmitDev
   // (a second read of an 8-byte record is far cheaper than a second sort window over all records).
   int ntx;                  // tile groups per map row: ceil(ntile / 2^gshift)
   int gshift;
+  // Passes with at most HIST_BINS bins: the record kernel counts its region's records per bin in shared memory and writes the
+  // column of SortDev::region_hist itself (no bin_histogram_kernel: no second pass over the keys).  nullptr otherwise.
+  unsigned *region_hist;    // [nbins][nregions]
+  int nregions, nbins;
 };
+constexpr int HIST_BINS = 1024; // 4 KB per record-kernel CTA: 2048^2 maps in up to 6 planes (169 tiles each)
 
 struct SortDev
 {

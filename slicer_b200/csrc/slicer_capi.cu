@@ -1043,6 +1043,11 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
     E.ntx = ntx;
     E.gshift = gshift;
     const int nregions = grid;
+    // few bins (one sort window of at most HIST_BINS): the record kernel counts its region's records per bin itself
+    const bool k1_hist = nbins <= binned::HIST_BINS && nbins <= binned::MAX_BINS;
+    E.region_hist = k1_hist ? h->bin.region_hist : nullptr;
+    E.nregions = nregions;
+    E.nbins = nbins;
     if ((unsigned long long)nregions * E.region_cap > h->bin.capacity)
       return fail("binned deposit: record buffer too small (internal error)");
     binned::SortDev Q;
@@ -1068,7 +1073,8 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
     {
       Q.bin_lo = lo;
       Q.nbins = nbins - lo < wbins ? nbins - lo : wbins;
-      binned::bin_histogram_kernel<<<nregions, binned::SCATTER_THREADS, 0, h->compute>>>(Q);
+      if (!k1_hist)
+        binned::bin_histogram_kernel<<<nregions, binned::SCATTER_THREADS, 0, h->compute>>>(Q);
       binned::bin_region_scan_kernel<<<Q.nbins, 1024, 0, h->compute>>>(Q);
       binned::bin_scan_kernel<<<1, 1024, 0, h->compute>>>(Q);
       binned::launch_bin_scatter(Q, nwin > 1, h->compute);
@@ -1081,7 +1087,7 @@ static int binned_pass(slicer_handle *h, const PassParams &P, const SegmentDev &
         else
           binned::tile_deposit_kernel<SLICER_MAS_TSC><<<Q.nbins << gshift, binned::DEPOSIT_THREADS, binned::TCELLS * 8, h->compute>>>(P, Q, nt, ntx, gshift, D.type, D.const_mass);
       }
-      h->stats.launches += 4;
+      h->stats.launches += k1_hist ? 3 : 4;
     }
     CU(cudaGetLastError());
     h->stats.launches += 1;
@@ -1372,6 +1378,8 @@ static int run_pass(slicer_handle *h, const slicer_plane_desc *planes, int nplan
     fill_segment(h, h->segs[si], &D);
     if (D.n == 0)
       continue;
+    if (D.mass && D.n >> 32) // (the kernels carry a particle's index to its mass in 32 bits)
+      return fail("slicer_deposit: a segment with per-particle masses holds %llu particles; stage it in batches of fewer than 2^32", D.n);
     if (kernel == SLICER_KERNEL_PIPELINED)
     {
       const int ub = use_binned(h, P, D);
