@@ -1,15 +1,18 @@
 """Turns the ncu captures of tools/profile_lightcone.py into the committed summaries under profiles/:
    gpurun_out/r02_launches_<wl>.csv + r02_profile_meta_<wl>.json -> profiles/r02_traffic_<wl>.json, profiles/r02_launches_<wl>.csv
    gpurun_out/r02_full_<wl>.ncu-rep                              -> profiles/r02_ncu_full_summary_<wl>.md
-usage: python tools/summarize_r02.py [workload, default c3]"""
+usage: python tools/summarize_r02.py [workload, default c3] [suffix]
+   with a suffix (e.g. _sparse) only gpurun_out/r02_full_<wl><suffix>.ncu-rep -> profiles/r02_ncu_full_summary_<wl><suffix>.md is made
+   (a full-set capture of other groups of the same light cone: PGROUPS=0 ... -o gpurun_out/r02_full_c3_sparse)"""
 import collections, csv, json, os, subprocess, sys
 
 wlname = sys.argv[1] if len(sys.argv) > 1 else "c3"
+suffix = sys.argv[2] if len(sys.argv) > 2 else ""
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 go, pr = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 meta = json.load(open(f"{go}/r02_profile_meta_{wlname}.json"))
 src = f"{go}/r02_launches_{wlname}.csv"
-if os.path.exists(src):
+if os.path.exists(src) and not suffix:
     rows = list(csv.DictReader(l for l in open(src) if l.startswith('"')))
     launch = collections.OrderedDict()
     for r in rows:
@@ -46,7 +49,7 @@ if os.path.exists(src):
     print("groups", n, "avg ms/pass", round(tot_ms / n, 3), "avg dram GB/pass", round(tot_dram / n, 2), "x algorithmic", round(tot_dram * 1e9 / n / meta["bytes_per_pass"], 3),
           {k: round(v / tot_ms, 3) for k, v in share.items()})
 
-rep = f"{go}/r02_full_{wlname}.ncu-rep"
+rep = f"{go}/r02_full_{wlname}{suffix}.ncu-rep"
 if os.path.exists(rep):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
@@ -63,7 +66,7 @@ if os.path.exists(rep):
     out = [f"# Round 02 — `ncu --set full` of the pass kernels ({wlname}, CUDA sources {meta['csrc_sha']})", "",
            "Command (after the same command exited 0 without ncu): `PGROUPS=<dense group> ncu --set full --clock-control none --import-source on "
            "--profile-from-start off -k regex:\"deposit_pipelined|bin_histogram|bin_scatter|tile_deposit\" -c 4 python tools/profile_lightcone.py`", "",
-           "Captured launches: the kernels of the densest group's pass (one slice).  Times under ncu are cold-cache and serialised.", "",
+           ("Captured launches: the kernels of the densest group's pass (one slice)." if not suffix else f"Captured launches: the pass kernels of the groups named by the capture ({suffix.strip('_')}).") + "  Times under ncu are cold-cache and serialised.", "",
            "| metric | " + " | ".join(f"launch {i}" for i in range(len(rows) - 2)) + " |", "|---|" + "---|" * (len(rows) - 2)]
 
     def fmt(v):
@@ -77,5 +80,5 @@ if os.path.exists(rep):
             i = hdr.index(w)
             label = w.replace("smsp__average_warps_issue_stalled_", "stall: ").replace("_per_issue_active.ratio", " (warps per issue)")
             out.append("| " + label + (" [" + units[i] + "]" if units[i] else "") + " | " + " | ".join(fmt(r[i]) for r in rows[2:]) + " |")
-    open(f"{pr}/r02_ncu_full_summary_{wlname}.md", "w").write("\n".join(out) + "\n")
+    open(f"{pr}/r02_ncu_full_summary_{wlname}{suffix}.md", "w").write("\n".join(out) + "\n")
     print("\n".join(out[6:14]))
